@@ -1,0 +1,318 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/zkmpc_oracle.c).
+
+ORACLE — TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; the shipped package (zk-mpc_b200/) never
+imports this module.
+
+All field elements are Montgomery-form little-endian u64 limbs exactly as arkworks'
+`Fp256.0.0` / `Fp384.0.0`: Fr = (n,4) uint64, Fq = (n,6), Fq2 = (n,12),
+G1 affine = (n,12) x|y + (n,) uint8 infinity flags, G2 affine = (n,24) x.c0|x.c1|y.c0|y.c1.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libzkmpc_oracle.so")
+
+u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc only, no external deps)."""
+    srcs = [os.path.join(_HERE, f) for f in ("zkmpc_oracle.c", "field_tmpl.h", "curve_tmpl.h", "Makefile")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    r = subprocess.run(["make", "-C", _HERE, "-B"], capture_output=True, text=True)
+    if r.returncode != 0:
+        # toolchains without libgomp: same code, windows processed serially
+        r = subprocess.run(["make", "-C", _HERE, "-B", "OMP="], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_domain_params.restype = C.c_int
+        _lib.orc_ntt_fr.restype = C.c_int
+        _lib.orc_g1_on_curve.restype = C.c_int
+        _lib.orc_g2_on_curve.restype = C.c_int
+    return _lib
+
+
+def _a(x, cols=None):
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    if cols is not None:
+        assert x.shape[-1] == cols, (x.shape, cols)
+    return x
+
+
+def _p(x):
+    return x.ctypes.data_as(u64p)
+
+
+def _p8(x):
+    return x.ctypes.data_as(u8p)
+
+
+def _inf(inf, n):
+    if inf is None:
+        return np.zeros(n, dtype=np.uint8)
+    return np.ascontiguousarray(inf, dtype=np.uint8)
+
+
+# ----------------------------------------------------------------------------- fields
+_OPS = {"add": 0, "sub": 1, "mul": 2, "neg": 3, "inv": 4, "from_mont": 5, "to_mont": 6, "sqr": 7}
+
+
+def _vec(fn, limbs, op, a, b=None):
+    a = _a(a, limbs)
+    out = np.empty_like(a)
+    if b is not None:
+        b = _a(b, limbs)
+        assert b.shape == a.shape
+    n = a.size // limbs
+    fn(C.c_int(_OPS[op]), _p(a), _p(b) if b is not None else None, _p(out), C.c_size_t(n))
+    return out
+
+
+def fr(op, a, b=None):
+    return _vec(lib().orc_fr_vec, 4, op, a, b)
+
+
+def fq(op, a, b=None):
+    return _vec(lib().orc_fq_vec, 6, op, a, b)
+
+
+def fq2(op, a, b=None):
+    return _vec(lib().orc_fq2_vec, 12, op, a, b)
+
+
+def fr_batch_inv(a):
+    a = _a(a, 4).copy()
+    lib().orc_fr_batch_inv(_p(a), C.c_size_t(a.size // 4))
+    return a
+
+
+def constants():
+    names = ["fr_mod", "fr_r", "fr_r2", "fr_gen", "fr_root", "fq_mod", "fq_r", "fq_r2"]
+    bufs = [np.zeros(4 if k.startswith("fr") else 6, dtype=np.uint64) for k in names]
+    lib().orc_constants(*[_p(b) for b in bufs])
+    return dict(zip(names, bufs))
+
+
+# ----------------------------------------------------------------------------- G1
+def g1_generator():
+    out = np.zeros(12, dtype=np.uint64)
+    lib().orc_g1_generator(_p(out))
+    return out
+
+
+def g1_on_curve(xy, inf=0):
+    xy = _a(xy, 12)
+    return bool(lib().orc_g1_on_curve(_p(xy), C.c_uint8(int(inf))))
+
+
+def g1_scalar_mul(xy, k_limbs, inf=0):
+    xy = _a(xy, 12)
+    k = _a(k_limbs)
+    out = np.zeros(12, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g1_scalar_mul(_p(xy), C.c_uint8(int(inf)), _p(k), C.c_int(k.size), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+def g1_add(a_xy, b_xy, a_inf=0, b_inf=0):
+    a_xy, b_xy = _a(a_xy, 12), _a(b_xy, 12)
+    out = np.zeros(12, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g1_add(_p(a_xy), C.c_uint8(int(a_inf)), _p(b_xy), C.c_uint8(int(b_inf)), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+def g1_sum_jac(pts):
+    pts = _a(pts, 18)
+    out = np.zeros(12, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g1_sum_jac(_p(pts), C.c_size_t(pts.size // 18), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+def g1_generate(seed, n, first=0):
+    out = np.zeros((n, 12), dtype=np.uint64)
+    lib().orc_g1_generate(C.c_uint64(seed), C.c_size_t(first), C.c_size_t(n), _p(out))
+    return out
+
+
+def g1_msm(bases_xy, scalars_mont, inf=None, threads=1):
+    bases_xy, scalars_mont = _a(bases_xy, 12), _a(scalars_mont, 4)
+    n = min(bases_xy.size // 12, scalars_mont.size // 4)      # variable_base.rs:16-18
+    inf = _inf(inf, bases_xy.size // 12)
+    out = np.zeros(12, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g1_msm(_p(bases_xy), _p8(inf), _p(scalars_mont), C.c_size_t(n), _p(out), C.byref(oinf),
+                     C.c_int(threads))
+    return out, oinf.value
+
+
+def g1_msm_naive(bases_xy, scalars_mont, inf=None):
+    bases_xy, scalars_mont = _a(bases_xy, 12), _a(scalars_mont, 4)
+    n = min(bases_xy.size // 12, scalars_mont.size // 4)
+    inf = _inf(inf, bases_xy.size // 12)
+    out = np.zeros(12, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g1_msm_naive(_p(bases_xy), _p8(inf), _p(scalars_mont), C.c_size_t(n), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+# ----------------------------------------------------------------------------- G2
+def g2_coeff_b():
+    out = np.zeros(12, dtype=np.uint64)
+    lib().orc_g2_coeff_b(_p(out))
+    return out
+
+
+def g2_on_curve(xy, inf=0):
+    xy = _a(xy, 24)
+    return bool(lib().orc_g2_on_curve(_p(xy), C.c_uint8(int(inf))))
+
+
+def g2_scalar_mul(xy, k_limbs, inf=0):
+    xy = _a(xy, 24)
+    k = _a(k_limbs)
+    out = np.zeros(24, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g2_scalar_mul(_p(xy), C.c_uint8(int(inf)), _p(k), C.c_int(k.size), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+def g2_add(a_xy, b_xy, a_inf=0, b_inf=0):
+    a_xy, b_xy = _a(a_xy, 24), _a(b_xy, 24)
+    out = np.zeros(24, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g2_add(_p(a_xy), C.c_uint8(int(a_inf)), _p(b_xy), C.c_uint8(int(b_inf)), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+def g2_generate(gen_xy, seed, n, first=0):
+    gen_xy = _a(gen_xy, 24)
+    out = np.zeros((n, 24), dtype=np.uint64)
+    lib().orc_g2_generate(_p(gen_xy), C.c_uint64(seed), C.c_size_t(first), C.c_size_t(n), _p(out))
+    return out
+
+
+def g2_msm(bases_xy, scalars_mont, inf=None, threads=1):
+    bases_xy, scalars_mont = _a(bases_xy, 24), _a(scalars_mont, 4)
+    n = min(bases_xy.size // 24, scalars_mont.size // 4)
+    inf = _inf(inf, bases_xy.size // 24)
+    out = np.zeros(24, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g2_msm(_p(bases_xy), _p8(inf), _p(scalars_mont), C.c_size_t(n), _p(out), C.byref(oinf),
+                     C.c_int(threads))
+    return out, oinf.value
+
+
+def g2_msm_naive(bases_xy, scalars_mont, inf=None):
+    bases_xy, scalars_mont = _a(bases_xy, 24), _a(scalars_mont, 4)
+    n = min(bases_xy.size // 24, scalars_mont.size // 4)
+    inf = _inf(inf, bases_xy.size // 24)
+    out = np.zeros(24, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    lib().orc_g2_msm_naive(_p(bases_xy), _p8(inf), _p(scalars_mont), C.c_size_t(n), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+# ----------------------------------------------------------------------------- domain / NTT
+KIND = {"fft": 0, "ifft": 1, "coset_fft": 2, "coset_ifft": 3}
+
+
+def domain_params(log_n):
+    out = np.zeros((5, 4), dtype=np.uint64)
+    ok = lib().orc_domain_params(C.c_uint(log_n), _p(out))
+    if not ok:
+        raise ValueError("domain too large")
+    return dict(group_gen=out[0], group_gen_inv=out[1], size_inv=out[2], generator_inv=out[3], size_as_fe=out[4])
+
+
+def ntt(data, kind):
+    """In-order transform of a (2^k,4) Montgomery Fr array; returns a new array."""
+    data = _a(data, 4).copy()
+    n = data.size // 4
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    rc = lib().orc_ntt_fr(_p(data), C.c_uint(log_n), C.c_uint(KIND[kind] if isinstance(kind, str) else kind))
+    if rc:
+        raise ValueError("orc_ntt_fr rc=%d" % rc)
+    return data
+
+
+def divide_by_vanishing_on_coset(data):
+    data = _a(data, 4).copy()
+    n = data.size // 4
+    lib().orc_divide_by_vanishing_on_coset(_p(data), C.c_uint(n.bit_length() - 1))
+    return data
+
+
+def horner(coeffs, point):
+    coeffs, point = _a(coeffs, 4), _a(point, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_fr_horner(_p(coeffs), C.c_size_t(coeffs.size // 4), _p(point), _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- Beaver
+def beaver_mask(s, x):
+    s, x = _a(s, 4), _a(x, 4)
+    out = np.empty_like(s)
+    lib().orc_beaver_mask(_p(s), _p(x), _p(out), C.c_size_t(s.size // 4))
+    return out
+
+
+def beaver_combine(x, y, z, sx, oy, is_leader, spdz=False):
+    """additive: x,y,z (n,4).  SPDZ: x,y,z (2,n,4) = [sh plane, mac plane]; sx,oy always (n,4)."""
+    x, y, z, sx, oy = _a(x, 4), _a(y, 4), _a(z, 4), _a(sx, 4), _a(oy, 4)
+    n = sx.size // 4
+    assert x.size // 4 == (2 * n if spdz else n)
+    out = np.empty_like(x)
+    lib().orc_beaver_combine(_p(x), _p(y), _p(z), _p(sx), _p(oy), _p(out), C.c_size_t(n),
+                             C.c_uint(int(bool(is_leader))), C.c_uint(int(bool(spdz))))
+    return out
+
+
+def open_sum(parts):
+    parts = _a(parts, 4)
+    P, n = parts.shape[0], parts.shape[1]
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().orc_open_sum(_p(parts), C.c_uint(P), _p(out), C.c_size_t(n))
+    return out
+
+
+def spdz_mac_check(vals, macs, is_leader):
+    vals, macs = _a(vals, 4), _a(macs, 4)
+    out = np.empty_like(vals)
+    lib().orc_spdz_mac_check(_p(vals), _p(macs), _p(out), C.c_size_t(vals.size // 4), C.c_uint(int(bool(is_leader))))
+    return out
+
+
+VEC_OP = {"sub": 0, "mul": 1, "mul_const": 2, "axpy": 3}
+
+
+def vec_op(op, a, b=None, c=None):
+    a = _a(a, 4)
+    b = _a(b, 4) if b is not None else None
+    c = _a(c, 4) if c is not None else None
+    out = np.empty_like(a)
+    lib().orc_vec_op(C.c_uint(VEC_OP[op]), _p(a), _p(b) if b is not None else None,
+                     _p(c) if c is not None else None, _p(out), C.c_size_t(a.size // 4))
+    return out

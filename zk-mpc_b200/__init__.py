@@ -1,0 +1,9 @@
+"""zk-mpc_b200 — B200-native share-MSM / share-NTT / Beaver kernels behind a C ABI.
+
+Layout: csrc/ (hand-written sm_100a CUDA + the extern "C" boundary declared in
+include/mpc_cuda.h), build.py (nvcc recipe), _lib.py (ctypes binding that fails loudly
+when libmpc_cuda.so is absent), host.py (host-side mirror of the reference's operator
+interface), synth.py (seeded synthetic inputs).  The directory name carries a hyphen, so
+import it through `__graft_entry__.load_package()` (module name `zk_mpc_b200`).
+"""
+from . import synth  # noqa: F401
