@@ -1,0 +1,170 @@
+/*
+ * mpc_cuda.h — C ABI of libmpc_cuda.so, the B200 (sm_100a) implementation of zk-mpc's per-party
+ * prover hot path: share MSM, share NTT and the local halves of Beaver multiplication.
+ *
+ * This is the boundary a thin Rust crate (`mpc-cuda`) binds with
+ * `extern "C"`; each entry point names the reference interface it replaces (paths relative to the
+ * zk-mpc repository).  Conventions:
+ *   - every field element is Montgomery-form little-endian u64 limbs exactly as stored in
+ *     arkworks' Fp256.0.0 / Fp384.0.0 (Fr = 4 limbs, Fq = 6 limbs, Fq2 = c0|c1 = 12 limbs);
+ *   - G1 affine point = x|y (12 limbs) + one infinity byte; G2 affine = x.c0|x.c1|y.c0|y.c1
+ *     (24 limbs) + one infinity byte; affine zero is (0, 1, infinity = 1) as in
+ *     arkworks/algebra/ec/src/models/short_weierstrass_jacobian.rs:167-169;
+ *   - pointers are HOST memory unless the function name ends in `_dev` (device pointers on the
+ *     calling thread's current mpc_cuda device; `stream` is a cudaStream_t passed as void*,
+ *     NULL = the library's per-thread stream); the caller owns every buffer;
+ *   - return value 0 = OK; non-zero = error (mpc_cuda_last_error() describes it).  The reference
+ *     panics on failure (assert!/unwrap), so the Rust shim turns non-zero into panic!;
+ *   - host-pointer calls are synchronous; `_dev` calls are asynchronous on `stream`;
+ *   - any function may be called concurrently from several host threads (one per party under
+ *     mpc-net's LocalTestNet, mpc-net/src/multi.rs:436-441); party/device selection is per thread.
+ * There is no CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef MPC_CUDA_H
+#define MPC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_CUDA_OK 0
+#define MPC_CUDA_ERR_CUDA 1       /* a CUDA runtime call failed */
+#define MPC_CUDA_ERR_ARG 2        /* invalid argument */
+#define MPC_CUDA_ERR_NO_DEVICE 3  /* no CUDA device / init not possible */
+#define MPC_CUDA_ERR_HANDLE 4     /* unknown handle */
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Select the devices the library may use (NULL/0 = all visible).  Idempotent, thread-safe. */
+int32_t mpc_cuda_init(const int32_t* devices, int32_t n_dev);
+/* Party identity of the calling thread: leader = party 0 (mpc-net/src/lib.rs:49-51); the thread's
+ * default device becomes devices[party_id % n_dev]. */
+int32_t mpc_cuda_set_party(uint32_t party_id, uint32_t n_parties);
+/* Explicit device for the calling thread (index into the init list). */
+int32_t mpc_cuda_set_device(int32_t dev_index);
+int32_t mpc_cuda_device_count(void);
+const char* mpc_cuda_last_error(void);
+const char* mpc_cuda_version(void);
+
+/* device memory helpers for resident pipelines (the fused witness-map path, benchmarks) */
+int32_t mpc_cuda_malloc(void** dptr, size_t bytes);
+int32_t mpc_cuda_free(void* dptr);
+int32_t mpc_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream);
+int32_t mpc_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream);
+int32_t mpc_cuda_stream_sync(void* stream);
+
+/* ---- Beaver multiplication, local halves ----------------------------------------------------
+ * FieldShare::batch_mul (mpc-algebra/src/share/field.rs:97-129) =
+ *   mask (local) -> batch_open (network) -> mask (local) -> batch_open -> combine (local). */
+
+/* out[i] = s[i] + x[i]   (share/field.rs:108-117, FieldShare::add additive.rs:132-135 /
+ * spdz.rs:197-201).  SPDZ shares: pass the sh plane and the mac plane as one 2n-element call. */
+int32_t mpc_cuda_beaver_mask(const uint64_t* s, const uint64_t* x, uint64_t* out, size_t n);
+int32_t mpc_cuda_beaver_mask_dev(const uint64_t* s, const uint64_t* x, uint64_t* out, size_t n, void* stream);
+
+/* out = z - y*sx - x*oy (+ sx*oy on the leader)   (share/field.rs:118-128; scale/sub/shift of
+ * additive.rs:136-152, spdz.rs:202-219).  x, y, z are the party's triple shares, sx/oy the opened
+ * masked values.  spdz = 0: x,y,z,out hold n elements.  spdz = 1: x,y,z,out hold 2n elements laid
+ * out as [sh plane | mac plane]; sx/oy always n; the mac plane receives mac_share*sx*oy with
+ * mac_share = is_leader ? 1 : 0 (spdz.rs:31-38). */
+int32_t mpc_cuda_beaver_combine(const uint64_t* x, const uint64_t* y, const uint64_t* z,
+                                const uint64_t* sx_pub, const uint64_t* oy_pub, uint64_t* out,
+                                size_t n, uint32_t is_leader, uint32_t spdz);
+int32_t mpc_cuda_beaver_combine_dev(const uint64_t* x, const uint64_t* y, const uint64_t* z,
+                                    const uint64_t* sx_pub, const uint64_t* oy_pub, uint64_t* out,
+                                    size_t n, uint32_t is_leader, uint32_t spdz, void* stream);
+
+/* out[i] = sum_p parts[p*n + i]: the local half of batch_open after the broadcast
+ * (share/additive.rs:125-131, spdz.rs:181-184). */
+int32_t mpc_cuda_open_sum(const uint64_t* parts, uint32_t n_parties, uint64_t* out, size_t n);
+int32_t mpc_cuda_open_sum_dev(const uint64_t* parts, uint32_t n_parties, uint64_t* out, size_t n, void* stream);
+
+/* SPDZ MAC check, local half: out[i] = mac_share*vals[i] - macs[i]   (share/spdz.rs:185-189) */
+int32_t mpc_cuda_spdz_mac_check(const uint64_t* vals, const uint64_t* macs, uint64_t* out, size_t n,
+                                uint32_t is_leader);
+int32_t mpc_cuda_spdz_mac_check_dev(const uint64_t* vals, const uint64_t* macs, uint64_t* out, size_t n,
+                                    uint32_t is_leader, void* stream);
+
+/* Elementwise helpers used around the NTTs (src/groth16.rs:298-302, poly/src/domain/mod.rs:183-190,
+ * poly/src/polynomial/univariate/dense.rs:345-372):
+ *   MPC_CUDA_VEC_SUB        out = a - b
+ *   MPC_CUDA_VEC_MUL        out = a * b          (public x share / batch product of publics)
+ *   MPC_CUDA_VEC_MUL_CONST  out = a * c[0]
+ *   MPC_CUDA_VEC_AXPY       out = a + c[0] * b */
+#define MPC_CUDA_VEC_SUB 0
+#define MPC_CUDA_VEC_MUL 1
+#define MPC_CUDA_VEC_MUL_CONST 2
+#define MPC_CUDA_VEC_AXPY 3
+int32_t mpc_cuda_vec_op(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                        uint64_t* out, size_t n);
+int32_t mpc_cuda_vec_op_dev(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c_host,
+                            uint64_t* out, size_t n, void* stream);
+
+/* ---- share NTT ------------------------------------------------------------------------------
+ * Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place over Fr
+ * (arkworks/algebra/poly/src/domain/radix2/mod.rs:99-114, radix2/fft.rs:22-35,
+ * domain/mod.rs:138-141).  In-order input, in-order output; `data` holds `batch` vectors of
+ * 2^log_n elements back to back and is transformed in place.  With MpcField coefficients the
+ * transform of a party's local values IS its output share vector. */
+#define MPC_CUDA_NTT_FFT 0
+#define MPC_CUDA_NTT_IFFT 1
+#define MPC_CUDA_NTT_COSET_FFT 2
+#define MPC_CUDA_NTT_COSET_IFFT 3
+int32_t mpc_cuda_ntt_fr(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch);
+int32_t mpc_cuda_ntt_fr_dev(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch, void* stream);
+/* evals[i] *= (g^n - 1)^-1, g = 22  (EvaluationDomain::divide_by_vanishing_poly_on_coset_in_place) */
+int32_t mpc_cuda_divide_by_vanishing_on_coset(uint64_t* data, uint32_t log_n);
+int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n, void* stream);
+
+/* ---- share MSM ------------------------------------------------------------------------------
+ * Msm::msm / AffineMsm::msm (mpc-algebra/src/share/msm.rs:6-9,33-37) =
+ * AffineCurve::multi_scalar_mul (arkworks/algebra/ec/src/lib.rs:305-314: into_repr each scalar) +
+ * VariableBaseMSM::multi_scalar_mul (ec/src/msm/variable_base.rs:12-106) + into affine.
+ * n = min(bases, scalars) is decided by the caller (variable_base.rs:16-18).  `inf` may be NULL
+ * (no infinity bases).  The result is the affine point in Montgomery limbs + infinity byte. */
+int32_t mpc_cuda_msm_g1(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars_mont,
+                        size_t n, uint64_t out_xy[12], uint8_t* out_inf);
+int32_t mpc_cuda_msm_g2(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars_mont,
+                        size_t n, uint64_t out_xy[24], uint8_t* out_inf);
+
+/* Keep a CRS vector resident (pk.{a,b_g1,h,l}_query of src/groth16.rs:106-160, powers_of_g of
+ * arkworks/poly-commit/src/kzg10/mod.rs:166-170): only scalars cross PCIe afterwards. */
+int32_t mpc_cuda_msm_g1_register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle);
+int32_t mpc_cuda_msm_g1_register_bases_dev(const uint64_t* bases_xy_dev, size_t n, uint64_t* handle);
+int32_t mpc_cuda_msm_g2_register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle);
+int32_t mpc_cuda_msm_release_bases(uint64_t handle);
+/* MSM over bases[offset .. offset+n) of a registered vector; scalars on the host */
+int32_t mpc_cuda_msm_g1_handle(uint64_t handle, size_t offset, const uint64_t* scalars_mont, size_t n,
+                               uint64_t out_xy[12], uint8_t* out_inf);
+int32_t mpc_cuda_msm_g2_handle(uint64_t handle, size_t offset, const uint64_t* scalars_mont, size_t n,
+                               uint64_t out_xy[24], uint8_t* out_inf);
+/* scalars already on the device; writes the Jacobian partial (x,y,z = 18 limbs, z = 0 for infinity)
+ * to device memory without normalising, so per-GPU partials can be gathered and added
+ * (multi-GPU point-range sharding) */
+int32_t mpc_cuda_msm_g1_handle_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
+                                   uint64_t* out_jac_dev /*18*/, void* stream);
+/* affine(sum of `count` Jacobian partials); partials on the device, result on the host */
+int32_t mpc_cuda_g1_sum_partials_dev(const uint64_t* jac_dev /*count*18*/, uint32_t count,
+                                     uint64_t out_xy[12], uint8_t* out_inf, void* stream);
+
+/* Synthetic CRS for benchmarks and tests: bases[i] = k_i * G1 generator with
+ * k_i = max(1, mix64(seed + (first+i+1)*0x9E3779B97F4A7C15)), written as affine x|y to device memory. */
+int32_t mpc_cuda_g1_generate_dev(uint64_t seed, size_t first, size_t n, uint64_t* out_xy_dev, void* stream);
+int32_t mpc_cuda_g2_generate_dev(uint64_t seed, size_t first, size_t n, uint64_t* out_xy_dev, void* stream);
+
+/* ---- diagnostics ----------------------------------------------------------------------------
+ * Raw field kernels (one element per thread) used by the parity tests to pin the device
+ * arithmetic itself: field 0 = Fr (4 limbs), 1 = Fq (6 limbs); op 0 add, 1 sub, 2 mul, 3 neg,
+ * 4 inverse (0 -> 0), 5 Montgomery->canonical, 6 canonical->Montgomery, 7 square. */
+int32_t mpc_cuda_field_op(uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* Integer-pipe microbenchmark: returns achieved giga-ops/s of `iters` dependent instructions per
+ * thread over a full-chip grid.  kind 0 = IMAD.U32 (32-bit), 1 = IMAD.WIDE.U32 with carry chain,
+ * 2 = Fq Montgomery products (result in products/s), 3 = Fr Montgomery products. */
+int32_t mpc_cuda_microbench(uint32_t kind, uint32_t iters, double* gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_CUDA_H */

@@ -7,3 +7,6 @@ interface), synth.py (seeded synthetic inputs).  The directory name carries a hy
 import it through `__graft_entry__.load_package()` (module name `zk_mpc_b200`).
 """
 from . import synth  # noqa: F401
+from . import build as build_recipe  # noqa: F401
+from . import _lib  # noqa: F401
+from . import host  # noqa: F401

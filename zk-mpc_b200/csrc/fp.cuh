@@ -1,0 +1,337 @@
+// Multi-limb Montgomery prime-field arithmetic on 32-bit limbs for sm_100a.
+//
+// Replaces (computes the same function as) the reference's 64-bit-limb CIOS code:
+//   mul_assign        arkworks/algebra/ff/src/fields/arithmetic.rs:7-57
+//   square_in_place   arkworks/algebra/ff/src/fields/arithmetic.rs:85-172
+//   into_repr         arkworks/algebra/ff/src/fields/arithmetic.rs:59-83
+//   add/sub/neg/dbl   arkworks/algebra/ff/src/fields/macros.rs:317-323,638-651,698-717
+//   from_repr         arkworks/algebra/ff/src/fields/macros.rs:464-474
+// R = 2^(32 N) equals the reference's 2^(64 N/2), so Montgomery bit patterns are identical and
+// every value handed in or out is fully reduced in [0, p): results are bit-exact with the CPU path.
+//
+// Multiplication keeps the running total as two interleaved accumulators of 64-bit columns
+// (`ev` aligned to even limbs, `od` to odd limbs) so each 32x32->64 product is one
+// IMAD.WIDE.U32 with carry (mad.lo.cc + madc.hi.cc pair), 2N^2 wide MADs + O(N) per product.
+#pragma once
+#include "ptx.cuh"
+
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t v[N];
+
+    HD static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    HD static Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+        return r;
+    }
+    HD static Fp modulus() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::mod(i);
+        return r;
+    }
+    HD bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i];
+        return acc == 0;
+    }
+    HD bool operator==(const Fp& o) const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i] ^ o.v[i];
+        return acc == 0;
+    }
+    HD bool operator!=(const Fp& o) const { return !(*this == o); }
+};
+
+namespace fp_detail {
+
+// acc[0..n) += a[0], a[2], a[4] ... * b as 64-bit columns; leaves the carry-out in CC
+template <int n>
+HD void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t b) {
+    acc[0] = ptx::mad_lo_cc(a[0], b, acc[0]);
+    acc[1] = ptx::madc_hi_cc(a[0], b, acc[1]);
+#pragma unroll
+    for (int j = 2; j < n; j += 2) {
+        acc[j] = ptx::madc_lo_cc(a[j], b, acc[j]);
+        acc[j + 1] = ptx::madc_hi_cc(a[j], b, acc[j + 1]);
+    }
+}
+
+// same with the modulus as the multiplicand: acc += p[off], p[off+2], ... * m
+template <class P, int off>
+HD void cmad_mod(uint32_t* acc, uint32_t m) {
+    constexpr int n = P::N;
+    acc[0] = ptx::mad_lo_cc(P::mod(off), m, acc[0]);
+    acc[1] = ptx::madc_hi_cc(P::mod(off), m, acc[1]);
+#pragma unroll
+    for (int j = 2; j < n; j += 2) {
+        acc[j] = ptx::madc_lo_cc(P::mod(off + j), m, acc[j]);
+        acc[j + 1] = ptx::madc_hi_cc(P::mod(off + j), m, acc[j + 1]);
+    }
+}
+
+// One Montgomery reduction step on (ev, od): adds m*p so that ev[0] becomes 0.
+// The od chain cannot carry out (total < 2^(32(N+1))); the ev chain's carry lands on limb N = od[N-1].
+template <class P>
+HD void redc_row(uint32_t* ev, uint32_t* od) {
+    constexpr int N = P::N;
+    uint32_t m = ptx::mul_lo(ev[0], P::INV);
+    cmad_mod<P, 1>(od, m);
+    cmad_mod<P, 0>(ev, m);
+    od[N - 1] = ptx::addc(od[N - 1], 0);
+}
+
+// First row: ev = a_even * b, od = a_odd * b (no carries between disjoint 64-bit columns).
+template <int N>
+HD void mul_row_first(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t b) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        ev[j] = ptx::mul_lo(a[j], b);
+        ev[j + 1] = ptx::mul_hi(a[j], b);
+        od[j] = ptx::mul_lo(a[j + 1], b);
+        od[j + 1] = ptx::mul_hi(a[j + 1], b);
+    }
+}
+
+// Subsequent rows.  On entry the total is  ev_prev + od_prev * 2^32  with ev_prev[0] == 0.
+// Dividing by 2^32 turns od_prev into the new even-aligned accumulator `ev` and
+// (ev_prev >> 64) into the new odd-aligned accumulator, stored in place in `od`;
+// the stray limb ev_prev[1] is folded into ev[0], its carry entering the odd chain at limb 1.
+template <int N>
+HD void mul_row(uint32_t* ev /* = od_prev */, uint32_t* od /* = ev_prev */, const uint32_t* a, uint32_t b) {
+    ev[0] = ptx::add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        od[j] = ptx::madc_lo_cc(a[j + 1], b, od[j + 2]);
+        od[j + 1] = ptx::madc_hi_cc(a[j + 1], b, od[j + 3]);
+    }
+    od[N - 2] = ptx::madc_lo_cc(a[N - 1], b, 0);
+    od[N - 1] = ptx::madc_hi(a[N - 1], b, 0);
+    cmad_n<N>(ev, a, b);
+    od[N - 1] = ptx::addc(od[N - 1], 0);
+}
+
+// r = (r >= p) ? r - p : r
+template <class P>
+HD void final_sub(uint32_t* r) {
+    constexpr int N = P::N;
+    uint32_t t[N];
+    t[0] = ptx::sub_cc(r[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(r[i], P::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);      // 0xffffffff when r < p
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+}  // namespace fp_detail
+
+// 32-bit formulation (mad.lo.cc/madc.hi.cc): ptxas 12.9 lowers it to IMAD + IMAD.HI.U32.X + IADD3.X,
+// about 3 instructions per limb product.  Kept for A/B measurements (bench_fp kernels).
+template <class P>
+HD Fp<P> mul_narrow(const Fp<P>& a, const Fp<P>& b) {
+    using namespace fp_detail;
+    constexpr int N = P::N;
+    uint32_t ev[N], od[N];
+    mul_row_first<N>(ev, od, a.v, b.v[0]);
+    redc_row<P>(ev, od);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mul_row<N>(od, ev, a.v, b.v[i]);        // roles swap every row
+        redc_row<P>(od, ev);
+        if (i + 1 < N) {
+            mul_row<N>(ev, od, a.v, b.v[i + 1]);
+            redc_row<P>(ev, od);
+        }
+    }
+    // N is even: after the last (odd-indexed) row the even-aligned accumulator lives in `od`
+    // and holds a zero low limb; result = ev + (od >> 32)
+    Fp<P> r;
+    r.v[0] = ptx::add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(ev[i], od[i + 1]);
+    r.v[N - 1] = ptx::addc(ev[N - 1], 0);
+    final_sub<P>(r.v);
+    return r;
+}
+
+namespace fp_detail {
+
+HD uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+HD uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+HD uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// 64-bit-column formulation: ev[k] is the column at limbs (2k, 2k+1), od[k] at (2k+1, 2k+2).
+// Every limb product is one IMAD.WIDE.U32[.X] (see ptx.cuh).
+template <class P>
+HD void wredc_row(uint64_t* ev, uint64_t* od) {
+    constexpr int H = P::N / 2;
+    uint32_t m = ptx::mul_lo(lo32(ev[0]), P::INV);
+    od[0] = ptx::madw_cc(P::mod(1), m, od[0]);
+#pragma unroll
+    for (int k = 1; k < H; k++) od[k] = ptx::madwc_cc(P::mod(2 * k + 1), m, od[k]);   // no carry out
+    ev[0] = ptx::madw_cc(P::mod(0), m, ev[0]);
+#pragma unroll
+    for (int k = 1; k < H; k++) ev[k] = ptx::madwc_cc(P::mod(2 * k), m, ev[k]);
+    od[H - 1] = pack64(lo32(od[H - 1]), ptx::addc(hi32(od[H - 1]), 0));                  // carry -> limb N
+}
+
+template <int N>
+HD void wmul_row_first(uint64_t* ev, uint64_t* od, const uint32_t* a, uint32_t b) {
+#pragma unroll
+    for (int k = 0; k < N / 2; k++) {
+        ev[k] = ptx::mulw(a[2 * k], b);
+        od[k] = ptx::mulw(a[2 * k + 1], b);
+    }
+}
+
+// ev = od_prev, od = ev_prev (ev_prev's low limb is zero); see mul_row above for the derivation
+template <int N>
+HD void wmul_row(uint64_t* ev, uint64_t* od, const uint32_t* a, uint32_t b) {
+    constexpr int H = N / 2;
+    ev[0] = pack64(ptx::add_cc(lo32(ev[0]), hi32(od[0])), hi32(ev[0]));   // stray limb; carry enters limb 1
+#pragma unroll
+    for (int k = 0; k < H - 1; k++) od[k] = ptx::madwc_cc(a[2 * k + 1], b, od[k + 1]);
+    od[H - 1] = ptx::madwc(a[N - 1], b, 0);
+    ev[0] = ptx::madw_cc(a[0], b, ev[0]);
+#pragma unroll
+    for (int k = 1; k < H; k++) ev[k] = ptx::madwc_cc(a[2 * k], b, ev[k]);
+    od[H - 1] = pack64(lo32(od[H - 1]), ptx::addc(hi32(od[H - 1]), 0));
+}
+
+}  // namespace fp_detail
+
+template <class P>
+HD Fp<P> mul_wide(const Fp<P>& a, const Fp<P>& b) {
+    using namespace fp_detail;
+    constexpr int N = P::N, H = N / 2;
+    uint64_t ev[H], od[H];
+    wmul_row_first<N>(ev, od, a.v, b.v[0]);
+    wredc_row<P>(ev, od);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        wmul_row<N>(od, ev, a.v, b.v[i]);
+        wredc_row<P>(od, ev);
+        if (i + 1 < N) {
+            wmul_row<N>(ev, od, a.v, b.v[i + 1]);
+            wredc_row<P>(ev, od);
+        }
+    }
+    // result = ev + (od >> 32), od's low limb being zero
+    Fp<P> r;
+    r.v[0] = ptx::add_cc(lo32(ev[0]), hi32(od[0]));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) {
+        uint32_t e = (i & 1) ? hi32(ev[i / 2]) : lo32(ev[i / 2]);
+        uint32_t o = ((i + 1) & 1) ? hi32(od[(i + 1) / 2]) : lo32(od[(i + 1) / 2]);
+        r.v[i] = ptx::addc_cc(e, o);
+    }
+    r.v[N - 1] = ptx::addc(hi32(ev[H - 1]), 0);
+    final_sub<P>(r.v);
+    return r;
+}
+
+template <class P>
+HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
+#ifdef FP_MUL_NARROW
+    return mul_narrow(a, b);
+#else
+    return mul_wide(a, b);
+#endif
+}
+
+template <class P>
+HD Fp<P> sqr(const Fp<P>& a) {
+    return mul(a, a);
+}
+
+template <class P>
+HD Fp<P> add(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    r.v[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);      // p has spare top bits: no overflow
+    fp_detail::final_sub<P>(r.v);
+    return r;
+}
+
+template <class P>
+HD Fp<P> sub(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = ptx::subc(0, 0);      // all-ones when a < b
+    r.v[0] = ptx::add_cc(r.v[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(r.v[i], P::mod(i) & borrow);
+    r.v[N - 1] = ptx::addc(r.v[N - 1], P::mod(N - 1) & borrow);
+    return r;
+}
+
+template <class P>
+HD Fp<P> dbl(const Fp<P>& a) {
+    return add(a, a);
+}
+
+template <class P>
+HD Fp<P> neg(const Fp<P>& a) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.v[0] = ptx::sub_cc(P::mod(0), a.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::subc_cc(P::mod(i), a.v[i]);
+    r.v[N - 1] = ptx::subc(P::mod(N - 1), a.v[N - 1]);
+    uint32_t keep = a.is_zero() ? 0u : 0xffffffffu;       // -0 = 0
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] &= keep;
+    return r;
+}
+
+// Montgomery form -> canonical integer: one Montgomery product with 1 (value * R^-1)
+template <class P>
+HD Fp<P> from_mont(const Fp<P>& a) {
+    Fp<P> one_raw = Fp<P>::zero();
+    one_raw.v[0] = 1;
+    return mul(a, one_raw);
+}
+
+// canonical integer (< p) -> Montgomery form
+template <class P>
+HD Fp<P> to_mont(const Fp<P>& a) {
+    Fp<P> r2;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r2.v[i] = P::r2(i);
+    return mul(a, r2);
+}
+
+// a^(p-2) by square-and-multiply over the constant exponent; 0 -> 0.
+// (The reference uses binary Euclid, macros.rs:389-443; the value is the same.)
+template <class P>
+HD Fp<P> inv(const Fp<P>& a) {
+    constexpr int N = P::N;
+    Fp<P> acc = Fp<P>::one();
+    bool started = false;
+    for (int i = N * 32 - 1; i >= 0; i--) {
+        uint32_t bit = (P::pm2(i / 32) >> (i % 32)) & 1u;      // exponent p - 2
+        if (started) acc = sqr(acc);
+        if (bit) {
+            acc = mul(acc, a);
+            started = true;
+        }
+    }
+    return acc;
+}
