@@ -6,32 +6,107 @@
 #include <string.h>
 #include "consts.cuh"
 #include "fp.cuh"
+#include "fp2.cuh"
+#include "ec.cuh"
+#include "msm_digits.cuh"
 
 using Fr = Fp<consts::FrParams>;
 using Fq = Fp<consts::FqParams>;
+using Fq2 = Fp2<consts::FqParams>;
 
 template <class F>
 static void vec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
     constexpr int N = F::N;
     for (size_t i = 0; i < n; i++) {
         F x, y, r;
-        memcpy(x.v, a + N * i, 4 * N);
-        if (b) memcpy(y.v, b + N * i, 4 * N);
+        memcpy(&x, a + N * i, 4 * N);
+        if (b) memcpy(&y, b + N * i, 4 * N);
         switch (op) {
             case 0: r = add(x, y); break;
             case 1: r = sub(x, y); break;
             case 2: r = mul(x, y); break;
             case 3: r = neg(x); break;
             case 4: r = inv(x); break;
-            case 5: r = from_mont(x); break;
-            case 6: r = to_mont(x); break;
-            default: r = sqr(x); break;
+            case 7: r = sqr(x); break;
+            case 9: r = dbl(x); break;
+            default: r = x; break;
         }
-        memcpy(out + N * i, r.v, 4 * N);
+        memcpy(out + N * i, &r, 4 * N);
     }
 }
 
+template <class F>
+static void vec_op_mont(int op, const uint32_t* a, uint32_t* out, size_t n) {
+    constexpr int N = F::N;
+    for (size_t i = 0; i < n; i++) {
+        F x, r;
+        memcpy(&x, a + N * i, 4 * N);
+        r = op == 5 ? from_mont(x) : to_mont(x);
+        memcpy(out + N * i, &r, 4 * N);
+    }
+}
+
+// sum_i (+-)P_i three ways: a madd chain; two half chains joined by xyzz_add; the madd chain sent
+// through Jacobian and back and doubled-and-halved via xyzz_add with itself (exercises dbl).
+// out_xy[0]: chain, out_xy[1]: halves, out_xy[2]: (2*chain) via add(p,p)  (affine, N limbs x 2 each)
+template <class F>
+static void ec_sums(const uint32_t* pts, const uint8_t* negate, size_t n, uint32_t* out_xy, uint8_t* out_inf) {
+    constexpr int N = F::N;
+    XYZZ<F> acc = XYZZ<F>::infinity(), lo = XYZZ<F>::infinity(), hi = XYZZ<F>::infinity();
+    for (size_t i = 0; i < n; i++) {
+        F x, y;
+        memcpy(&x, pts + 2 * N * i, 4 * N);
+        memcpy(&y, pts + 2 * N * i + N, 4 * N);
+        if (negate && negate[i]) y = neg(y);
+        xyzz_madd(acc, x, y);
+        xyzz_madd(i < n / 2 ? lo : hi, x, y);
+    }
+    xyzz_add(lo, hi);
+    XYZZ<F> twice = jac_to_xyzz(xyzz_to_jac(acc));
+    XYZZ<F> same = twice;
+    xyzz_add(twice, same);
+    XYZZ<F>* res[3] = {&acc, &lo, &twice};
+    for (int k = 0; k < 3; k++) {
+        F ox, oy;
+        out_inf[k] = xyzz_to_affine(*res[k], ox, oy) ? 0 : 1;
+        memcpy(out_xy + 2 * N * k, &ox, 4 * N);
+        memcpy(out_xy + 2 * N * k + N, &oy, 4 * N);
+    }
+}
+
+template <class F>
+static void ec_mul_small(const uint32_t* pt, uint64_t k, uint32_t* out_xy, uint8_t* out_inf) {
+    constexpr int N = F::N;
+    XYZZ<F> p;
+    memcpy(&p.x, pt, 4 * N);
+    memcpy(&p.y, pt + N, 4 * N);
+    p.zz = F::one();
+    p.zzz = F::one();
+    XYZZ<F> r = xyzz_mul_small(p, k);
+    F ox, oy;
+    *out_inf = xyzz_to_affine(r, ox, oy) ? 0 : 1;
+    memcpy(out_xy, &ox, 4 * N);
+    memcpy(out_xy + N, &oy, 4 * N);
+}
+
 extern "C" {
-void emu_fr_vec(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) { vec_op<Fr>(op, a, b, out, n); }
-void emu_fq_vec(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) { vec_op<Fq>(op, a, b, out, n); }
+void emu_fr_vec(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    if (op == 5 || op == 6) vec_op_mont<Fr>(op, a, out, n); else vec_op<Fr>(op, a, b, out, n);
+}
+void emu_fq_vec(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    if (op == 5 || op == 6) vec_op_mont<Fq>(op, a, out, n); else vec_op<Fq>(op, a, b, out, n);
+}
+void emu_fq2_vec(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) { vec_op<Fq2>(op, a, b, out, n); }
+void emu_g1_sums(const uint32_t* pts, const uint8_t* negate, size_t n, uint32_t* out_xy, uint8_t* out_inf) { ec_sums<Fq>(pts, negate, n, out_xy, out_inf); }
+void emu_g2_sums(const uint32_t* pts, const uint8_t* negate, size_t n, uint32_t* out_xy, uint8_t* out_inf) { ec_sums<Fq2>(pts, negate, n, out_xy, out_inf); }
+void emu_g1_mul_small(const uint32_t* pt, uint64_t k, uint32_t* out_xy, uint8_t* out_inf) { ec_mul_small<Fq>(pt, k, out_xy, out_inf); }
+void emu_g2_mul_small(const uint32_t* pt, uint64_t k, uint32_t* out_xy, uint8_t* out_inf) { ec_mul_small<Fq2>(pt, k, out_xy, out_inf); }
+
+// signed-digit decomposition of canonical 256-bit scalars (msm_digits.cuh); out[w*n + i]
+void emu_signed_digits(const uint32_t* canon, size_t n, uint32_t c, uint32_t nwin, uint32_t* out) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < nwin; w++) out[(size_t)w * n + i] = msm::signed_digit(canon + 8 * i, w, c, nwin, carry);
+    }
+}
 }

@@ -1,0 +1,165 @@
+// Short-Weierstrass (a = 0) group law for BLS12-377 G1 (F = Fq) and G2 (F = Fq2) on the device.
+//
+// The reference accumulates in Jacobian coordinates
+//   add_assign_mixed  arkworks/algebra/ec/src/models/short_weierstrass_jacobian.rs:628-693
+//   add_assign        ...:721-783        double_in_place ...:557-600        into affine ...:823-845
+// and only the affine normal form of a sum is observable (mpc-algebra/src/share/msm.rs:33-37 converts
+// immediately), so the device is free to use extended Jacobian "XYZZ" coordinates
+// (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; infinity <=> ZZ = 0), whose mixed addition needs 8M + 2S instead
+// of 7M + 4S and whose accumulator start is a plain copy.  Formulas: EFD shortw/xyzz madd-2008-s,
+// add-2008-s, dbl-2008-s-1 (a = 0).  All exceptional cases (infinity, P + P, P - P) are handled, the
+// result is the exact group element, hence bit-identical to the CPU path after normalisation.
+#pragma once
+#include "fp.cuh"
+#include "fp2.cuh"
+
+template <class F>
+struct Affine {
+    F x, y;
+};
+
+template <class F>
+struct XYZZ {
+    F x, y, zz, zzz;
+    HD static XYZZ infinity() {
+        XYZZ r;
+        r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero();
+        return r;
+    }
+    HD bool is_inf() const { return zz.is_zero(); }
+};
+
+template <class F>
+struct Jac {
+    F x, y, z;      // x = X/Z^2, y = Y/Z^3; infinity <=> Z = 0 (the reference's zero() is (1,1,0))
+};
+
+// p = 2 * (qx, qy) for an affine point (never infinity; y != 0 on these prime-order-cofactor curves'
+// points we see, and y = 0 would correctly yield ZZ = 0 = infinity)
+template <class F>
+HD void xyzz_mdbl(XYZZ<F>& p, const F& qx, const F& qy) {
+    F u = dbl(qy);
+    F v = sqr(u);
+    F w = mul(u, v);
+    F s = mul(qx, v);
+    F xx = sqr(qx);
+    F m = add(dbl(xx), xx);
+    F x3 = sub(sqr(m), dbl(s));
+    p.y = sub(mul(m, sub(s, x3)), mul(w, qy));
+    p.x = x3;
+    p.zz = v;
+    p.zzz = w;
+}
+
+template <class F>
+HD void xyzz_dbl(XYZZ<F>& p) {
+    if (p.is_inf()) return;
+    F u = dbl(p.y);
+    F v = sqr(u);
+    F w = mul(u, v);
+    F s = mul(p.x, v);
+    F xx = sqr(p.x);
+    F m = add(dbl(xx), xx);
+    F x3 = sub(sqr(m), dbl(s));
+    F y3 = sub(mul(m, sub(s, x3)), mul(w, p.y));
+    p.x = x3;
+    p.y = y3;
+    p.zz = mul(v, p.zz);
+    p.zzz = mul(w, p.zzz);
+}
+
+// p += (qx, qy), the affine point being finite
+template <class F>
+HD void xyzz_madd(XYZZ<F>& p, const F& qx, const F& qy) {
+    if (p.is_inf()) {
+        p.x = qx; p.y = qy; p.zz = F::one(); p.zzz = F::one();
+        return;
+    }
+    F pp = sub(mul(qx, p.zz), p.x);       // P = U2 - X1
+    F r = sub(mul(qy, p.zzz), p.y);       // R = S2 - Y1
+    if (pp.is_zero()) {
+        if (r.is_zero()) xyzz_mdbl(p, qx, qy);
+        else p = XYZZ<F>::infinity();
+        return;
+    }
+    F p2 = sqr(pp);
+    F p3 = mul(pp, p2);
+    F q = mul(p.x, p2);
+    F x3 = sub(sub(sqr(r), p3), dbl(q));
+    p.y = sub(mul(r, sub(q, x3)), mul(p.y, p3));
+    p.x = x3;
+    p.zz = mul(p.zz, p2);
+    p.zzz = mul(p.zzz, p3);
+}
+
+// p += q (both XYZZ)
+template <class F>
+HD void xyzz_add(XYZZ<F>& p, const XYZZ<F>& q) {
+    if (q.is_inf()) return;
+    if (p.is_inf()) { p = q; return; }
+    F u1 = mul(p.x, q.zz);
+    F u2 = mul(q.x, p.zz);
+    F s1 = mul(p.y, q.zzz);
+    F s2 = mul(q.y, p.zzz);
+    F pp = sub(u2, u1);
+    F r = sub(s2, s1);
+    if (pp.is_zero()) {
+        if (r.is_zero()) xyzz_dbl(p);
+        else p = XYZZ<F>::infinity();
+        return;
+    }
+    F p2 = sqr(pp);
+    F p3 = mul(pp, p2);
+    F q2 = mul(u1, p2);
+    F x3 = sub(sub(sqr(r), p3), dbl(q2));
+    p.y = sub(mul(r, sub(q2, x3)), mul(s1, p3));
+    p.x = x3;
+    p.zz = mul(mul(p.zz, q.zz), p2);
+    p.zzz = mul(mul(p.zzz, q.zzz), p3);
+}
+
+// XYZZ -> Jacobian with Z = ZZ: (X*ZZ, Y*ZZZ, ZZ)   [x = X*ZZ/ZZ^2, y = Y*ZZZ/ZZ^3 = Y/ZZZ]
+template <class F>
+HD Jac<F> xyzz_to_jac(const XYZZ<F>& p) {
+    Jac<F> j;
+    if (p.is_inf()) { j.x = F::one(); j.y = F::one(); j.z = F::zero(); return j; }
+    j.x = mul(p.x, p.zz);
+    j.y = mul(p.y, p.zzz);
+    j.z = p.zz;
+    return j;
+}
+
+// Jacobian -> XYZZ: (X, Y, Z^2, Z^3)
+template <class F>
+HD XYZZ<F> jac_to_xyzz(const Jac<F>& j) {
+    XYZZ<F> p;
+    if (j.z.is_zero()) return XYZZ<F>::infinity();
+    p.x = j.x; p.y = j.y;
+    p.zz = sqr(j.z);
+    p.zzz = mul(p.zz, j.z);
+    return p;
+}
+
+// affine normal form; returns false (and the reference's affine zero (0, 1)) for infinity
+// (short_weierstrass_jacobian.rs:167-169,823-845)
+template <class F>
+HD bool xyzz_to_affine(const XYZZ<F>& p, F& ox, F& oy) {
+    if (p.is_inf()) { ox = F::zero(); oy = F::one(); return false; }
+    // one inversion: 1/(ZZ*ZZZ) -> 1/ZZ = that * ZZZ, 1/ZZZ = that * ZZ
+    F t = inv(mul(p.zz, p.zzz));
+    ox = mul(p.x, mul(t, p.zzz));
+    oy = mul(p.y, mul(t, p.zz));
+    return true;
+}
+
+// p = k * (qx, qy) for a small unsigned multiplier (double-and-add, MSB first)
+template <class F>
+HD XYZZ<F> xyzz_mul_small(const XYZZ<F>& q, uint64_t k) {
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    bool started = false;
+    for (int i = 63; i >= 0; i--) {
+        if (started) xyzz_dbl(acc);
+        if ((k >> i) & 1) { xyzz_add(acc, q); started = true; }
+    }
+    return acc;
+}
