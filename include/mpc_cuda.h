@@ -45,6 +45,17 @@ int32_t mpc_cuda_set_party(uint32_t party_id, uint32_t n_parties);
 /* Explicit device for the calling thread (index into the init list). */
 int32_t mpc_cuda_set_device(int32_t dev_index);
 int32_t mpc_cuda_device_count(void);
+/* Tuning knobs for benchmarks and tests (process-wide; 0 restores the automatic choice):
+ *   "msm_window_bits"  Pippenger window width c (3..16)
+ *   "msm_task_len"     maximum points one accumulation task adds (bucket splitting)
+ *   "profile"          1: bracket pipeline stages with CUDA events on the launching stream */
+int32_t mpc_cuda_set_option(const char* name, int64_t value);
+/* Number of kernels this library has launched so far (all threads). */
+uint64_t mpc_cuda_launch_count(void);
+/* Device time accumulated by the calling thread for a stage since the last read, and the number of
+ * intervals; waits for the pending events.  Stages: "msm_total", "msm_sort", "msm_accumulate",
+ * "msm_reduce", "ntt". */
+int32_t mpc_cuda_profile_read(const char* name, double* ms_total, uint64_t* count);
 const char* mpc_cuda_last_error(void);
 const char* mpc_cuda_version(void);
 

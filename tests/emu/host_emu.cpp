@@ -110,3 +110,26 @@ void emu_signed_digits(const uint32_t* canon, size_t n, uint32_t c, uint32_t nwi
     }
 }
 }
+
+// the k_generate loop of msm.cu (double-and-madd over a 64-bit multiplier) on the host
+template <class F>
+static void ec_generate(const uint32_t* gx, const uint32_t* gy, uint64_t k, uint32_t* out_xy) {
+    constexpr int N = F::N;
+    F x, y;
+    memcpy(&x, gx, 4 * N);
+    memcpy(&y, gy, 4 * N);
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    bool started = false;
+    for (int b = 63; b >= 0; b--) {
+        if (started) xyzz_dbl(acc);
+        if ((k >> b) & 1) { xyzz_madd(acc, x, y); started = true; }
+    }
+    F ox, oy;
+    xyzz_to_affine(acc, ox, oy);
+    memcpy(out_xy, &ox, 4 * N);
+    memcpy(out_xy + N, &oy, 4 * N);
+}
+extern "C" {
+void emu_g1_generate(uint64_t k, uint32_t* out_xy) { ec_generate<Fq>(consts::G1_GEN_X, consts::G1_GEN_Y, k, out_xy); }
+void emu_g2_generate(uint64_t k, uint32_t* out_xy) { ec_generate<Fq2>(consts::G2_GEN_X, consts::G2_GEN_Y, k, out_xy); }
+}

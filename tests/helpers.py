@@ -1,0 +1,39 @@
+"""Shared helpers of the parity tests (CPU side, exact integer arithmetic)."""
+import numpy as np
+
+import pyref as P
+
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def gen_ks(pkg, seed, n, first=0):
+    """the multipliers k_i of the synthetic CRS bases[i] = k_i * G (mpc_cuda_g1_generate_dev / orc_g1_generate)"""
+    with np.errstate(over="ignore"):
+        idx = np.arange(first + 1, first + n + 1, dtype=np.uint64)
+        k = pkg.synth._mix64(np.uint64(seed) + idx * _GOLD)
+    k[k == 0] = 1
+    return k
+
+
+def _pieces16(a):
+    return [((a >> np.uint64(16 * j)) & np.uint64(0xFFFF)) for j in range(4)]
+
+
+def dot_mod_r(scalars_mont, ks):
+    """(sum_i s_i * k_i) mod r for Montgomery-form Fr limbs (n,4) and uint64 multipliers, exactly:
+    16-bit pieces keep every partial dot product below 2^64 for n <= 2^32."""
+    scalars_mont = np.ascontiguousarray(scalars_mont, dtype=np.uint64)
+    kp = _pieces16(np.ascontiguousarray(ks, dtype=np.uint64))
+    total = 0
+    for limb in range(4):
+        lp = _pieces16(scalars_mont[:, limb])
+        for a in range(4):
+            for b in range(4):
+                total += int(np.dot(lp[a], kp[b])) << (64 * limb + 16 * (a + b))
+    return total * pow(P.FR_RR, -1, P.R_MOD) % P.R_MOD
+
+
+def expected_msm_of_generated(orc, scalars_mont, ks):
+    """affine (xy, inf) of (sum s_i k_i) * G through one oracle scalar multiplication"""
+    e = dot_mod_r(scalars_mont, ks)
+    return orc.g1_scalar_mul(orc.g1_generator(), np.array(P.to_limbs(e, 4), dtype=np.uint64))

@@ -39,9 +39,10 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.mpc_cuda_last_error.restype = C.c_char_p
         _lib.mpc_cuda_version.restype = C.c_char_p
+        _lib.mpc_cuda_launch_count.restype = C.c_uint64
         for name in declared_symbols():
             fn = getattr(_lib, name, None)
-            if fn is not None and name not in ("mpc_cuda_last_error", "mpc_cuda_version"):
+            if fn is not None and name not in ("mpc_cuda_last_error", "mpc_cuda_version", "mpc_cuda_launch_count"):
                 fn.restype = C.c_int32
     return _lib
 

@@ -27,6 +27,13 @@ void set_error(const char* fmt, ...);
         }                                                                                        \
     } while (0)
 
+// after every kernel launch: surface launch errors and count the launch (mpc_cuda_launch_count)
+#define MPC_KERNEL_CHECK()                          \
+    do {                                            \
+        MPC_CUDA_TRY(cudaGetLastError());           \
+        mpc::count_launch();                        \
+    } while (0)
+
 #define MPC_TRY(expr)                  \
     do {                               \
         int32_t _rc = (expr);          \
@@ -51,7 +58,26 @@ struct DeviceInfo {
 // per-thread stream.  Every exported entry point starts with this.
 int32_t enter(cudaStream_t* stream_out);
 const DeviceInfo* current_device_info();
+int current_device_index();      // index into the init list (per-device caches are keyed by it)
 bool is_leader();
+
+void count_launch();
+
+// stage timing with CUDA events on the launching stream, active while option "profile" is 1; read and
+// reset with mpc_cuda_profile_read (bench.py uses it for the per-kernel roofline numbers)
+void profile_begin(const char* name, cudaStream_t s);
+void profile_end(const char* name, cudaStream_t s);
+struct ProfileScope {
+    const char* name;
+    cudaStream_t s;
+    ProfileScope(const char* n, cudaStream_t st) : name(n), s(st) { profile_begin(name, s); }
+    ~ProfileScope() { profile_end(name, s); }
+};
+
+// tuning knobs set through mpc_cuda_set_option (0 = automatic)
+extern int64_t g_opt_msm_window_bits;
+extern int64_t g_opt_msm_task_len;
+extern int64_t g_opt_profile;
 
 inline cudaStream_t pick_stream(void* user, cudaStream_t mine) { return user ? (cudaStream_t)user : mine; }
 

@@ -1,7 +1,10 @@
 // Context, error reporting and memory helpers of libmpc_cuda.so (include/mpc_cuda.h, "context").
 #include <stdarg.h>
 
+#include <atomic>
+#include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -86,6 +89,57 @@ const DeviceInfo* current_device_info() {
     return &g_devices[t_dev_index];
 }
 
+int current_device_index() { return t_dev_index; }
+
+int64_t g_opt_profile = 0;
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// pending (start, stop) event pairs of the calling thread, folded into per-name totals on read
+struct Pending {
+    std::string name;
+    cudaEvent_t e0, e1;
+    bool closed;
+};
+static thread_local std::vector<Pending> t_pending;
+static thread_local std::map<std::string, std::pair<double, uint64_t>> t_totals;
+
+void profile_begin(const char* name, cudaStream_t s) {
+    if (!g_opt_profile) return;
+    Pending p;
+    p.name = name;
+    p.closed = false;
+    if (cudaEventCreate(&p.e0) != cudaSuccess || cudaEventCreate(&p.e1) != cudaSuccess) return;
+    cudaEventRecord(p.e0, s);
+    t_pending.push_back(p);
+}
+
+void profile_end(const char* name, cudaStream_t s) {
+    if (!g_opt_profile) return;
+    for (size_t i = t_pending.size(); i-- > 0;) {
+        if (!t_pending[i].closed && t_pending[i].name == name) {
+            cudaEventRecord(t_pending[i].e1, s);
+            t_pending[i].closed = true;
+            return;
+        }
+    }
+}
+
+static void profile_fold() {
+    for (Pending& p : t_pending) {
+        if (p.closed && cudaEventSynchronize(p.e1) == cudaSuccess) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+                t_totals[p.name].first += ms;
+                t_totals[p.name].second += 1;
+            }
+        }
+        cudaEventDestroy(p.e0);
+        cudaEventDestroy(p.e1);
+    }
+    t_pending.clear();
+}
+
 bool is_leader() { return t_party == 0; }
 
 }  // namespace mpc
@@ -125,6 +179,35 @@ int32_t mpc_cuda_device_count(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (init_locked(nullptr, 0) != MPC_CUDA_OK) return 0;
     return (int32_t)g_devices.size();
+}
+
+int32_t mpc_cuda_set_option(const char* name, int64_t value) {
+    MPC_ARG_CHECK(name != nullptr);
+    if (!strcmp(name, "msm_window_bits")) {
+        MPC_ARG_CHECK(value >= 0 && value <= 16);
+        g_opt_msm_window_bits = value;
+    } else if (!strcmp(name, "profile")) {
+        g_opt_profile = value ? 1 : 0;
+    } else if (!strcmp(name, "msm_task_len")) {
+        MPC_ARG_CHECK(value >= 0 && value <= (1 << 20));
+        g_opt_msm_task_len = value;
+    } else {
+        set_error("unknown option '%s'", name);
+        return MPC_CUDA_ERR_ARG;
+    }
+    return MPC_CUDA_OK;
+}
+
+uint64_t mpc_cuda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int32_t mpc_cuda_profile_read(const char* name, double* ms_total, uint64_t* count) {
+    MPC_ARG_CHECK(name && ms_total && count);
+    profile_fold();
+    auto it = t_totals.find(name);
+    *ms_total = it == t_totals.end() ? 0.0 : it->second.first;
+    *count = it == t_totals.end() ? 0 : it->second.second;
+    if (it != t_totals.end()) t_totals.erase(it);
+    return MPC_CUDA_OK;
 }
 
 const char* mpc_cuda_last_error(void) { return t_err; }

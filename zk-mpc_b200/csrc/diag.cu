@@ -42,7 +42,7 @@ int32_t field_op(uint32_t op, const uint64_t* a, const uint64_t* b, uint64_t* ou
         MPC_CUDA_TRY(cudaMemcpyAsync(db, b, n * sizeof(F), cudaMemcpyHostToDevice, s));
     }
     k_field_op<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(op, da, db, dout, n);
-    MPC_CUDA_TRY(cudaGetLastError());
+    MPC_KERNEL_CHECK();
     MPC_CUDA_TRY(cudaMemcpyAsync(out, dout, n * sizeof(F), cudaMemcpyDeviceToHost, s));
     MPC_CUDA_TRY(cudaStreamSynchronize(s));
     return MPC_CUDA_OK;
@@ -137,7 +137,7 @@ int32_t mpc_cuda_microbench(uint32_t kind, uint32_t iters, double* gops) {
             case 4: k_mb_mul<Fq, true><<<blocks, MB_THREADS, 0, s>>>(iters, (const Fq*)buf, (Fq*)sink); per_thread = iters; break;
             default: k_mb_mul<Fr, true><<<blocks, MB_THREADS, 0, s>>>(iters, (const Fr*)buf, (Fr*)sink); per_thread = iters; break;
         }
-        MPC_CUDA_TRY(cudaGetLastError());
+        MPC_KERNEL_CHECK();
         MPC_CUDA_TRY(cudaEventRecord(e1, s));
         MPC_CUDA_TRY(cudaEventSynchronize(e1));
     }

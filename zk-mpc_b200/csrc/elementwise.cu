@@ -121,7 +121,7 @@ int32_t mpc_cuda_beaver_mask_dev(const uint64_t* s_, const uint64_t* x, uint64_t
     if (n == 0) return MPC_CUDA_OK;
     MPC_ARG_CHECK(s_ && x && out);
     k_mask<<<ew_grid(n), EW_THREADS, 0, pick_stream(stream, s)>>>((const Fr*)s_, (const Fr*)x, (Fr*)out, n);
-    MPC_CUDA_TRY(cudaGetLastError());
+    MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
 }
 
@@ -157,7 +157,7 @@ int32_t mpc_cuda_beaver_combine_dev(const uint64_t* x, const uint64_t* y, const 
         if (spdz) k_combine<false, true><<<g, EW_THREADS, 0, st>>>(fx, fy, fz, fsx, foy, fo, n);
         else k_combine<false, false><<<g, EW_THREADS, 0, st>>>(fx, fy, fz, fsx, foy, fo, n);
     }
-    MPC_CUDA_TRY(cudaGetLastError());
+    MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
 }
 
@@ -189,7 +189,7 @@ int32_t mpc_cuda_open_sum_dev(const uint64_t* parts, uint32_t P, uint64_t* out, 
     if (n == 0) return MPC_CUDA_OK;
     MPC_ARG_CHECK(parts && out);
     k_open_sum<<<ew_grid(n), EW_THREADS, 0, pick_stream(stream, s)>>>((const Fr*)parts, P, (Fr*)out, n);
-    MPC_CUDA_TRY(cudaGetLastError());
+    MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
 }
 
@@ -216,7 +216,7 @@ int32_t mpc_cuda_spdz_mac_check_dev(const uint64_t* vals, const uint64_t* macs, 
     cudaStream_t st = pick_stream(stream, s);
     if (is_leader) k_mac_check<true><<<ew_grid(n), EW_THREADS, 0, st>>>((const Fr*)vals, (const Fr*)macs, (Fr*)out, n);
     else k_mac_check<false><<<ew_grid(n), EW_THREADS, 0, st>>>((const Fr*)vals, (const Fr*)macs, (Fr*)out, n);
-    MPC_CUDA_TRY(cudaGetLastError());
+    MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
 }
 
@@ -256,7 +256,7 @@ int32_t mpc_cuda_vec_op_dev(uint32_t op, const uint64_t* a, const uint64_t* b, c
         case MPC_CUDA_VEC_MUL_CONST: k_vec_op<MPC_CUDA_VEC_MUL_CONST><<<g, EW_THREADS, 0, st>>>(fa, fb, c, fo, n); break;
         default: k_vec_op<MPC_CUDA_VEC_AXPY><<<g, EW_THREADS, 0, st>>>(fa, fb, c, fo, n); break;
     }
-    MPC_CUDA_TRY(cudaGetLastError());
+    MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
 }
 

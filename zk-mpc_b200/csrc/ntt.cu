@@ -1,0 +1,372 @@
+// Share NTT over Fr: in-order radix-2 transforms of Radix2EvaluationDomain, computed as multi-stage
+// shared-memory passes (decimation in frequency) with the bit reversal fused into the last pass.
+//
+// Replaces  fft_in_place / ifft_in_place / coset_ifft_in_place   arkworks/algebra/poly/src/domain/radix2/mod.rs:99-114
+//           coset_fft_in_place                                    arkworks/algebra/poly/src/domain/mod.rs:138-141
+//           io_helper / oi_helper / derange / roots_of_unity      arkworks/algebra/poly/src/domain/radix2/fft.rs:76-78,185-307
+//           distribute_powers_and_mul_by_const                    arkworks/algebra/poly/src/domain/mod.rs:98-105
+//           divide_by_vanishing_poly_on_coset_in_place            arkworks/algebra/poly/src/domain/mod.rs:183-190
+// The outputs are exact field elements of the uniquely defined transforms
+//   fft: out[i] = Σ a[j] ω^(ij);  ifft: out[i] = n⁻¹ Σ a[j] ω^(-ij);  coset variants pre/post-scale by 22^(±i),
+// so any correct evaluation order is bit-identical to the reference's io_helper/oi_helper loops.
+//
+// Layout of one pass over stages [s0, s0+deg):  element index i = hi·(n>>s0) + j·T + lo with
+// T = n >> (s0+deg); a CTA owns a tile of 2^deg rows (j) x C adjacent columns (lo), i.e. 128-byte
+// contiguous runs in HBM, keeps it in shared memory as 8 limb planes (bank-conflict-free for
+// consecutive elements), and runs `deg` butterfly stages on it.  The last pass (T = 1) gathers C
+// sub-transforms whose bit-reversed destinations are adjacent, so its stores are 128-byte runs too,
+// and fuses the n⁻¹ / coset scaling.  The index algebra is modelled and tested in tests/ntt_model.py.
+#include <mutex>
+
+#include "common.cuh"
+
+using namespace mpc;
+
+namespace {
+
+constexpr int NTT_MAX_DEG = 8;
+constexpr int NTT_LOG_C = 2;               // 4 adjacent 32-byte elements = one 128-byte line
+constexpr int COSET_LO_BITS = 12;
+constexpr int MAX_LOG_N = 30;
+
+// ---- small kernels that build the per-device constant tables (all arithmetic stays on the GPU) -----
+// consts[l] = ω_l (primitive 2^l-th root: TWO_ADIC_ROOT squared 47-l times, ff/src/fields/mod.rs:363-378)
+// consts[48+l] = (2^l)⁻¹ = size_inv,  consts[96+l] = (22^(2^l) - 1)⁻¹ (vanishing polynomial on the coset)
+__global__ void k_domain_consts(Fr root47, Fr two_inv, Fr gen, Fr* __restrict__ consts) {
+    uint32_t l = threadIdx.x;
+    if (l > 47) return;
+    Fr w = root47;
+    for (uint32_t i = l; i < 47; i++) w = sqr(w);
+    consts[l] = w;
+    Fr ni = Fr::one();
+    for (uint32_t i = 0; i < l; i++) ni = mul(ni, two_inv);
+    consts[48 + l] = ni;
+    Fr z = gen;
+    for (uint32_t i = 0; i < l; i++) z = sqr(z);
+    consts[96 + l] = inv(sub(z, Fr::one()));
+}
+
+// out[i] = (base^(2^pre))^i
+__global__ void __launch_bounds__(256) k_powers(const Fr* __restrict__ base_ptr, uint32_t pre, size_t count,
+                                                Fr* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr b = load_fe_ro(base_ptr);
+    for (uint32_t k = 0; k < pre; k++) b = sqr(b);
+    Fr acc = Fr::one();
+    bool started = false;
+    for (int bit = 63 - __clzll((unsigned long long)(i | 1)); bit >= 0; bit--) {
+        if (started) acc = sqr(acc);
+        if ((i >> bit) & 1) {
+            acc = started ? mul(acc, b) : b;
+            started = true;
+        }
+    }
+    store_fe(out + i, acc);
+}
+
+__global__ void __launch_bounds__(256) k_mul_const_dev(Fr* __restrict__ data, const Fr* __restrict__ c, size_t n) {
+    Fr k = load_fe_ro(c);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        store_fe(data + i, mul(load_fe(data + i), k));
+}
+
+// ---- the pass kernel ----------------------------------------------------------------------------------
+struct PassArgs {
+    const Fr* src;
+    Fr* dst;
+    const Fr* tw[NTT_MAX_DEG];     // tw[r] = forward table of domain l = log_n - s0 - r  (ω_l^i, i < 2^(l-1))
+    const Fr* pre_lo;              // coset_fft (first pass): x *= pre_lo[i & 4095] * pre_hi[i >> 12]
+    const Fr* pre_hi;
+    const Fr* post_lo;             // coset_ifft (last pass): x *= scale * post_lo[d & 4095] * post_hi[d >> 12]
+    const Fr* post_hi;
+    const Fr* scale;               // ifft / coset_ifft (last pass): n⁻¹
+    uint32_t log_n, s0, deg, lc;   // lc = log2(columns per tile)
+    uint32_t last, inverse;
+};
+
+DEV Fr sm_load(const uint32_t* sm, uint32_t E, uint32_t e) {
+    Fr r;
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.v[l] = sm[l * E + e];
+    return r;
+}
+DEV void sm_store(uint32_t* sm, uint32_t E, uint32_t e, const Fr& a) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) sm[l * E + e] = a.v[l];
+}
+DEV uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? __brev(x) >> (32 - bits) : 0; }
+
+__global__ void __launch_bounds__(512) k_ntt_pass(PassArgs a) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t t = threadIdx.x;
+    const uint32_t rows = 1u << a.deg, C = 1u << a.lc, E = rows << a.lc;
+    const size_t n = (size_t)1 << a.log_n;
+    const size_t T = n >> (a.s0 + a.deg);
+    const size_t tile = blockIdx.x;
+    const Fr* src = a.src + (size_t)blockIdx.y * n;
+    Fr* dst = a.dst + (size_t)blockIdx.y * n;
+
+    // tile origin: non-last: i = origin + j*T + c;  last: i = (hb + (bitrev(c) << (s0-lc))) * rows + j
+    size_t origin = 0, lo0 = 0, hb = 0;
+    if (!a.last) {
+        size_t tiles_per_hi = T >> a.lc;
+        size_t hi = tile / tiles_per_hi;
+        lo0 = (tile % tiles_per_hi) << a.lc;
+        origin = hi * (n >> a.s0) + lo0;
+    } else {
+        hb = bitrev((uint32_t)(tile << a.lc), a.s0);
+    }
+
+    // ---- load two elements per thread
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t e = t + h * (E / 2);
+        uint32_t j, c;
+        size_t i;
+        if (!a.last) {
+            j = e >> a.lc; c = e & (C - 1);
+            i = origin + (size_t)j * T + c;
+        } else {
+            c = e >> a.deg; j = e & (rows - 1);
+            i = ((hb + ((size_t)bitrev(c, a.lc) << (a.s0 - a.lc))) << a.deg) + j;
+        }
+        Fr x = load_fe(src + i);
+        if (a.pre_lo) {
+            x = mul(x, load_fe_ro(a.pre_lo + (i & ((1u << COSET_LO_BITS) - 1))));
+            if (a.log_n > COSET_LO_BITS) x = mul(x, load_fe_ro(a.pre_hi + (i >> COSET_LO_BITS)));
+        }
+        sm_store(sm, E, (j << a.lc) + c, x);
+    }
+    __syncthreads();
+
+    // ---- deg butterfly stages: lo' = lo + hi, hi' = (lo - hi) * w
+    const uint32_t c = t & (C - 1), q = t >> a.lc;
+    const size_t lo = a.last ? 0 : lo0 + c;
+    for (uint32_t r = 0; r < a.deg; r++) {
+        const uint32_t hbits = a.deg - 1 - r, half = 1u << hbits;
+        const uint32_t qq = q & (half - 1);
+        const uint32_t j0 = ((q >> hbits) << (hbits + 1)) | qq, j1 = j0 + half;
+        const uint32_t l = a.log_n - a.s0 - r;          // this stage is the first stage of a size-2^l DIF
+        size_t k = (size_t)qq * T + lo;
+        Fr u = sm_load(sm, E, (j0 << a.lc) + c), v = sm_load(sm, E, (j1 << a.lc) + c);
+        bool swap = a.inverse && k != 0;                 // ω^-k = -ω^(2^(l-1) - k)
+        if (swap) k = ((size_t)1 << (l - 1)) - k;
+        Fr d = swap ? sub(v, u) : sub(u, v);
+        if (l > 1) d = mul(d, load_fe_ro(a.tw[r] + k));  // l == 1: the only twiddle is 1
+        sm_store(sm, E, (j0 << a.lc) + c, add(u, v));
+        sm_store(sm, E, (j1 << a.lc) + c, d);
+        __syncthreads();
+    }
+
+    // ---- store
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t e = t + h * (E / 2);
+        uint32_t j = e >> a.lc, cc = e & (C - 1);
+        if (!a.last) {
+            store_fe(dst + origin + (size_t)j * T + cc, sm_load(sm, E, e));
+        } else {
+            // row j of the store is destination block j: source row bitrev(j)
+            Fr x = sm_load(sm, E, (bitrev(j, a.deg) << a.lc) + cc);
+            size_t d = ((size_t)j << a.s0) + (tile << a.lc) + cc;
+            if (a.scale) x = mul(x, load_fe_ro(a.scale));
+            if (a.post_lo) {
+                x = mul(x, load_fe_ro(a.post_lo + (d & ((1u << COSET_LO_BITS) - 1))));
+                if (a.log_n > COSET_LO_BITS) x = mul(x, load_fe_ro(a.post_hi + (d >> COSET_LO_BITS)));
+            }
+            store_fe(dst + d, x);
+        }
+    }
+}
+
+// n == 1: ifft / coset_ifft multiply by 1⁻¹ = 1, everything is the identity
+// ---- per-device domain cache ---------------------------------------------------------------------------
+struct DomainCache {
+    bool ready = false;
+    Fr* consts = nullptr;                  // 144 entries, see k_domain_consts
+    Fr* tw[MAX_LOG_N + 1] = {};            // forward twiddle tables by domain log-size
+    Fr *g_lo = nullptr, *gi_lo = nullptr;  // 22^i, 22^-i, i < 4096
+    Fr *g_hi = nullptr, *gi_hi = nullptr;  // 22^(±4096 h), h < 2^hi_bits
+    Fr* gen_pair = nullptr;                // [22, 22⁻¹]
+    uint32_t hi_bits = 0;
+};
+std::mutex g_ntt_mu;
+DomainCache g_cache[64];
+
+Fr fr_from_limbs(const uint32_t* l) {
+    Fr r;
+    memcpy(r.v, l, sizeof(r.v));
+    return r;
+}
+
+// make sure the tables a transform of size 2^log_n needs exist on the current device
+int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s, DomainCache** out) {
+    std::lock_guard<std::mutex> lk(g_ntt_mu);
+    DomainCache& d = g_cache[dev_index];
+    bool dirty = false;
+    if (!d.ready) {
+        MPC_CUDA_TRY(cudaMalloc((void**)&d.consts, 144 * sizeof(Fr)));
+        MPC_CUDA_TRY(cudaMalloc((void**)&d.gen_pair, 2 * sizeof(Fr)));
+        k_domain_consts<<<1, 64, 0, s>>>(fr_from_limbs(consts::FR_TWO_ADIC_ROOT), fr_from_limbs(consts::FR_TWO_INV),
+                                        fr_from_limbs(consts::FR_GENERATOR), d.consts);
+        MPC_KERNEL_CHECK();
+        Fr pair[2] = {fr_from_limbs(consts::FR_GENERATOR), fr_from_limbs(consts::FR_GENERATOR_INV)};
+        MPC_CUDA_TRY(cudaMemcpyAsync(d.gen_pair, pair, sizeof(pair), cudaMemcpyHostToDevice, s));
+        MPC_CUDA_TRY(cudaStreamSynchronize(s));       // `pair` is a stack buffer
+        d.ready = true;
+    }
+    for (uint32_t l = 2; l <= log_n; l++) {
+        if (d.tw[l]) continue;
+        size_t count = (size_t)1 << (l - 1);
+        MPC_CUDA_TRY(cudaMalloc((void**)&d.tw[l], count * sizeof(Fr)));
+        k_powers<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d.consts + l, 0, count, d.tw[l]);
+        MPC_KERNEL_CHECK();
+        dirty = true;
+    }
+    if (coset) {
+        const size_t lo_n = (size_t)1 << COSET_LO_BITS;
+        if (!d.g_lo) {
+            MPC_CUDA_TRY(cudaMalloc((void**)&d.g_lo, lo_n * sizeof(Fr)));
+            MPC_CUDA_TRY(cudaMalloc((void**)&d.gi_lo, lo_n * sizeof(Fr)));
+            k_powers<<<(unsigned)(lo_n / 256), 256, 0, s>>>(d.gen_pair, 0, lo_n, d.g_lo);
+            MPC_KERNEL_CHECK();
+            k_powers<<<(unsigned)(lo_n / 256), 256, 0, s>>>(d.gen_pair + 1, 0, lo_n, d.gi_lo);
+            MPC_KERNEL_CHECK();
+            dirty = true;
+        }
+        uint32_t need = log_n > COSET_LO_BITS ? log_n - COSET_LO_BITS : 0;
+        if (need && (!d.g_hi || need > d.hi_bits)) {
+            if (d.g_hi) {
+                MPC_CUDA_TRY(cudaDeviceSynchronize());      // other streams may still read the old tables
+                cudaFree(d.g_hi);
+                cudaFree(d.gi_hi);
+            }
+            size_t hi_n = (size_t)1 << need;
+            MPC_CUDA_TRY(cudaMalloc((void**)&d.g_hi, hi_n * sizeof(Fr)));
+            MPC_CUDA_TRY(cudaMalloc((void**)&d.gi_hi, hi_n * sizeof(Fr)));
+            k_powers<<<(unsigned)((hi_n + 255) / 256), 256, 0, s>>>(d.gen_pair, COSET_LO_BITS, hi_n, d.g_hi);
+            MPC_KERNEL_CHECK();
+            k_powers<<<(unsigned)((hi_n + 255) / 256), 256, 0, s>>>(d.gen_pair + 1, COSET_LO_BITS, hi_n, d.gi_hi);
+            MPC_KERNEL_CHECK();
+            d.hi_bits = need;
+            dirty = true;
+        }
+    }
+    // tables are shared by every stream of the device: publish them only once they are complete
+    if (dirty) MPC_CUDA_TRY(cudaStreamSynchronize(s));
+    *out = &d;
+    return MPC_CUDA_OK;
+}
+
+int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStream_t s) {
+    MPC_ARG_CHECK(kind <= MPC_CUDA_NTT_COSET_IFFT);
+    MPC_ARG_CHECK(log_n <= MAX_LOG_N && log_n <= (uint32_t)consts::FR_TWO_ADICITY);
+    if (batch == 0) return MPC_CUDA_OK;
+    MPC_ARG_CHECK(data != nullptr);
+    if (log_n == 0) return MPC_CUDA_OK;      // size-1 domain: every kind is the identity (size_inv = 1, g^0 = 1)
+    const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
+    const bool coset = kind >= MPC_CUDA_NTT_COSET_FFT;
+    DomainCache* d;
+    MPC_TRY(ensure_tables(current_device_index(), log_n, coset, s, &d));
+
+    ProfileScope prof("ntt", s);
+    const size_t n = (size_t)1 << log_n;
+    uint32_t npass = (log_n + NTT_MAX_DEG - 1) / NTT_MAX_DEG;
+    uint32_t base = log_n / npass, extra = log_n % npass;
+    Scratch stmp;
+    Fr* tmp = nullptr;
+    if (npass > 1) MPC_TRY(stmp.alloc(&tmp, n * batch, s));
+
+    uint32_t s0 = 0;
+    for (uint32_t p = 0; p < npass; p++) {
+        uint32_t deg = base + (p < extra ? 1 : 0);
+        bool first = p == 0, last = p + 1 == npass;
+        PassArgs a;
+        memset(&a, 0, sizeof(a));
+        a.src = first ? data : tmp;
+        a.dst = last ? data : tmp;
+        a.log_n = log_n; a.s0 = s0; a.deg = deg;
+        a.last = last; a.inverse = inverse;
+        for (uint32_t r = 0; r < deg; r++) a.tw[r] = d->tw[log_n - s0 - r];      // l = 1 entry is nullptr (unused)
+        size_t T = n >> (s0 + deg);
+        size_t tiles;
+        if (!last) {
+            uint32_t lc = NTT_LOG_C;
+            while (((size_t)1 << lc) > T) lc--;
+            a.lc = lc;
+            tiles = ((size_t)1 << s0) * (T >> lc);
+        } else {
+            a.lc = s0 < (uint32_t)NTT_LOG_C ? s0 : NTT_LOG_C;
+            tiles = ((size_t)1 << s0) >> a.lc;
+        }
+        if (first && kind == MPC_CUDA_NTT_COSET_FFT) { a.pre_lo = d->g_lo; a.pre_hi = d->g_hi; }
+        if (last && inverse) a.scale = d->consts + 48 + log_n;
+        if (last && kind == MPC_CUDA_NTT_COSET_IFFT) { a.post_lo = d->gi_lo; a.post_hi = d->gi_hi; }
+        uint32_t E = (1u << deg) << a.lc;
+        MPC_ARG_CHECK(tiles < ((size_t)1 << 31) && batch < 65536);
+        dim3 grid((unsigned)tiles, batch);
+        k_ntt_pass<<<grid, E / 2, (size_t)E * sizeof(Fr), s>>>(a);
+        MPC_KERNEL_CHECK();
+        s0 += deg;
+    }
+    return MPC_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mpc_cuda_ntt_fr_dev(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch, void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    return ntt_dev((Fr*)data, log_n, kind, batch, pick_stream(stream, s));
+}
+
+int32_t mpc_cuda_ntt_fr(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_ARG_CHECK(log_n <= MAX_LOG_N);
+    if (batch == 0) return MPC_CUDA_OK;
+    MPC_ARG_CHECK(data != nullptr);
+    size_t count = ((size_t)1 << log_n) * batch;
+    Scratch sd;
+    Fr* d;
+    MPC_TRY(sd.alloc(&d, count, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(d, data, count * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    MPC_TRY(ntt_dev(d, log_n, kind, batch, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(data, d, count * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    MPC_CUDA_TRY(cudaStreamSynchronize(s));
+    return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n, void* stream) {
+    cudaStream_t s0;
+    MPC_TRY(enter(&s0));
+    cudaStream_t s = pick_stream(stream, s0);
+    MPC_ARG_CHECK(data != nullptr && log_n <= MAX_LOG_N);
+    DomainCache* d;
+    MPC_TRY(ensure_tables(current_device_index(), 0, false, s, &d));
+    size_t n = (size_t)1 << log_n;
+    k_mul_const_dev<<<grid_for(n, 256, 8), 256, 0, s>>>((Fr*)data, d->consts + 96 + log_n, n);
+    MPC_KERNEL_CHECK();
+    return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_divide_by_vanishing_on_coset(uint64_t* data, uint32_t log_n) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_ARG_CHECK(data != nullptr && log_n <= MAX_LOG_N);
+    size_t n = (size_t)1 << log_n;
+    Scratch sd;
+    Fr* d;
+    MPC_TRY(sd.alloc(&d, n, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(d, data, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    MPC_TRY(mpc_cuda_divide_by_vanishing_on_coset_dev((uint64_t*)d, log_n, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(data, d, n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    MPC_CUDA_TRY(cudaStreamSynchronize(s));
+    return MPC_CUDA_OK;
+}
+
+}  // extern "C"

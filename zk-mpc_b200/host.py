@@ -121,3 +121,173 @@ def vec_op(op, a, b=None, c=None):
     out = np.empty_like(a)
     _lib.call("mpc_cuda_vec_op", C.c_uint32(VEC_OP[op]), _p(a), _p(b), _p(c), _p(out), C.c_size_t(a.size // 4))
     return out
+
+
+def set_option(name, value):
+    _lib.call("mpc_cuda_set_option", name.encode(), C.c_int64(int(value)))
+
+
+# ----------------------------------------------------------------------------- share NTT
+NTT_KIND = {"fft": 0, "ifft": 1, "coset_fft": 2, "coset_ifft": 3}
+
+
+def ntt(data, kind, batch=1):
+    """Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place on `batch` back-to-back vectors
+    (host arrays; returns a new array).  Like the reference, the caller zero-pads to the domain size."""
+    data = _a(data, 4).copy()
+    total = data.size // 4
+    if batch < 1 or total % batch:
+        raise ValueError("batch does not divide the element count")
+    n = total // batch
+    log_n = n.bit_length() - 1
+    if n == 0 or (1 << log_n) != n:
+        raise ValueError("domain size must be a power of two, got %d" % n)
+    _lib.call("mpc_cuda_ntt_fr", _p(data), C.c_uint32(log_n), C.c_uint32(NTT_KIND[kind] if isinstance(kind, str) else kind),
+              C.c_uint32(batch))
+    return data
+
+
+def divide_by_vanishing_on_coset(data):
+    data = _a(data, 4).copy()
+    n = data.size // 4
+    _lib.call("mpc_cuda_divide_by_vanishing_on_coset", _p(data), C.c_uint32(n.bit_length() - 1))
+    return data
+
+
+# ----------------------------------------------------------------------------- share MSM
+def _inf(inf, n):
+    if inf is None:
+        return None, None
+    inf = np.ascontiguousarray(inf, dtype=np.uint8)
+    if inf.size < n:
+        raise ValueError("infinity flags shorter than bases")
+    return inf, inf.ctypes.data_as(u8p)
+
+
+def _msm(fn, limbs, bases_xy, scalars_mont, inf):
+    bases_xy, scalars_mont = _a(bases_xy, limbs), _a(scalars_mont, 4)
+    n = min(bases_xy.size // limbs, scalars_mont.size // 4)       # variable_base.rs:16-18
+    keep, pinf = _inf(inf, n)
+    out = np.zeros(limbs, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    _lib.call(fn, _p(bases_xy), pinf, _p(scalars_mont), C.c_size_t(n), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+def msm_g1(bases_xy, scalars_mont, inf=None):
+    """AffineMsm::msm over G1 (mpc-algebra/src/share/msm.rs:33-37): affine result + infinity flag"""
+    return _msm("mpc_cuda_msm_g1", 12, bases_xy, scalars_mont, inf)
+
+
+def msm_g2(bases_xy, scalars_mont, inf=None):
+    return _msm("mpc_cuda_msm_g2", 24, bases_xy, scalars_mont, inf)
+
+
+class BaseHandle:
+    """A CRS vector kept resident on the calling thread's device (pk.*_query, powers_of_g)."""
+
+    def __init__(self, handle, n, g2):
+        self.handle, self.n, self.g2 = handle, n, g2
+
+    def release(self):
+        if self.handle:
+            _lib.call("mpc_cuda_msm_release_bases", C.c_uint64(self.handle))
+            self.handle = 0
+
+
+def register_bases(bases_xy, inf=None, g2=False):
+    limbs = 24 if g2 else 12
+    bases_xy = _a(bases_xy, limbs)
+    n = bases_xy.size // limbs
+    keep, pinf = _inf(inf, n)
+    h = C.c_uint64(0)
+    _lib.call("mpc_cuda_msm_g2_register_bases" if g2 else "mpc_cuda_msm_g1_register_bases", _p(bases_xy), pinf,
+              C.c_size_t(n), C.byref(h))
+    return BaseHandle(h.value, n, g2)
+
+
+def msm_handle(handle, scalars_mont, offset=0, n=None):
+    scalars_mont = _a(scalars_mont, 4)
+    if n is None:
+        n = min(handle.n - offset, scalars_mont.size // 4)
+    limbs = 24 if handle.g2 else 12
+    out = np.zeros(limbs, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    _lib.call("mpc_cuda_msm_g2_handle" if handle.g2 else "mpc_cuda_msm_g1_handle", C.c_uint64(handle.handle),
+              C.c_size_t(offset), _p(scalars_mont), C.c_size_t(n), _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+def multi_scale_pub_group(bases_xy, share_planes, inf=None, g2=False):
+    """GroupShare::multi_scale_pub_group.  Additive shares (mpc-algebra/src/share/additive.rs:517-520):
+    `share_planes` is (n,4) and the result one point.  SPDZ shares (share/spdz.rs:482-488): `share_planes`
+    is (2,n,4) = [sh, mac]; the reference builds BOTH scalar vectors from `sh` (line 484 reads s.sh.val for
+    the macs), so the mac component of the result equals the sh component — reproduced here by
+    computing the MSM once."""
+    planes = np.ascontiguousarray(share_planes, dtype=np.uint64)
+    fn = msm_g2 if g2 else msm_g1
+    if planes.ndim == 2:
+        return fn(bases_xy, planes, inf)
+    sh = fn(bases_xy, planes[0], inf)
+    return sh, sh
+
+
+# ----------------------------------------------------------------------------- device-resident helpers
+class DeviceBuffer:
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p(0)
+        self.nbytes = nbytes
+        _lib.call("mpc_cuda_malloc", C.byref(self.ptr), C.c_size_t(nbytes))
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _lib.call("mpc_cuda_memcpy_h2d", self.ptr, arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes), None)
+        _lib.call("mpc_cuda_stream_sync", None)
+        return self
+
+    def download(self, dtype=np.uint64, count=None):
+        out = np.empty(self.nbytes // np.dtype(dtype).itemsize if count is None else count, dtype=dtype)
+        _lib.call("mpc_cuda_memcpy_d2h", out.ctypes.data_as(C.c_void_p), self.ptr, C.c_size_t(out.nbytes), None)
+        _lib.call("mpc_cuda_stream_sync", None)
+        return out
+
+    def u64(self):
+        return C.cast(self.ptr, u64p)
+
+    def free(self):
+        if self.ptr:
+            _lib.call("mpc_cuda_free", self.ptr)
+            self.ptr = C.c_void_p(0)
+
+
+def g1_generate(seed, n, first=0):
+    """synthetic CRS on the device: bases[i] = k_i * G1 generator (same schedule as the oracle's generator)"""
+    buf = DeviceBuffer(max(n, 1) * 96)
+    _lib.call("mpc_cuda_g1_generate_dev", C.c_uint64(seed), C.c_size_t(first), C.c_size_t(n), buf.u64(), None)
+    _lib.call("mpc_cuda_stream_sync", None)
+    return buf
+
+
+def g2_generate(seed, n, first=0):
+    buf = DeviceBuffer(max(n, 1) * 192)
+    _lib.call("mpc_cuda_g2_generate_dev", C.c_uint64(seed), C.c_size_t(first), C.c_size_t(n), buf.u64(), None)
+    _lib.call("mpc_cuda_stream_sync", None)
+    return buf
+
+
+def register_bases_dev(buf, n):
+    h = C.c_uint64(0)
+    _lib.call("mpc_cuda_msm_g1_register_bases_dev", buf.u64(), C.c_size_t(n), C.byref(h))
+    return BaseHandle(h.value, n, False)
+
+
+def launch_count():
+    return int(_lib.lib().mpc_cuda_launch_count())
+
+
+def profile_read(name):
+    """(total device ms, intervals) of a profiled stage since the last read (option "profile" = 1)"""
+    ms, cnt = C.c_double(0), C.c_uint64(0)
+    _lib.call("mpc_cuda_profile_read", name.encode(), C.byref(ms), C.byref(cnt))
+    return ms.value, cnt.value
