@@ -10,3 +10,4 @@ from . import synth  # noqa: F401
 from . import build as build_recipe  # noqa: F401
 from . import _lib  # noqa: F401
 from . import host  # noqa: F401
+from . import sharding  # noqa: F401
