@@ -198,7 +198,10 @@ def run_gpu(args):
 
     # ---- synthetic inputs: bases k_i*G generated on the device, uniform ("share-like") scalars
     bases_dev = H.g1_generate(seed, n, first=rank * n)
+    plain = H.register_bases_dev(bases_dev, n)          # CRS resident, no table: 20-bit windows, 13 bucket sets
     handle = H.register_bases_dev(bases_dev, n)
+    if not args.no_table:
+        handle.precompute(0)                            # + 2^(cw)*P table (12 x 1.6 GB): one shared bucket set
     scalars_host = torch.from_numpy(S.fr_uniform(seed + 1000 * rank, n).view(np.int64)).pin_memory()
     scalars_dev = scalars_host.to("cuda", non_blocking=True)
     partial = torch.zeros(18, dtype=torch.int64, device="cuda")
@@ -207,8 +210,8 @@ def run_gpu(args):
     out_inf = C.c_uint8(0)
     torch.cuda.synchronize()
 
-    def step():
-        L.call("mpc_cuda_msm_g1_handle_dev", C.c_uint64(handle.handle), C.c_size_t(0),
+    def step(hd=None):
+        L.call("mpc_cuda_msm_g1_handle_dev", C.c_uint64((hd or handle).handle), C.c_size_t(0),
                C.cast(scalars_dev.data_ptr(), L.u64p), C.c_size_t(n), C.cast(partial.data_ptr(), L.u64p), sptr)
         if world > 1:
             dist.all_gather_into_tensor(gathered, partial)
@@ -243,6 +246,23 @@ def run_gpu(args):
         stage_ms[nm] = t / max(cnt, 1)
     ms_per_step = ms_total / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # the same step without the table (what a host-buffer call can use)
+    step(plain)
+    barrier()
+    H.set_option("profile", 1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(args.steps):
+        step(plain)
+    p1.record(stream)
+    barrier()
+    H.set_option("profile", 0)
+    plain_ms = max_over_ranks(p0.elapsed_time(p1)) / args.steps
+    plain_stage = {}
+    for nm in ("msm_total", "msm_sort", "msm_accumulate", "msm_reduce"):
+        t, cnt = H.profile_read(nm)
+        plain_stage[nm] = t / max(cnt, 1)
 
     # ---- integer-pipe roofline of the dominant kernel (k_accumulate), IMAD peak measured live
     imad_peak = max(H.microbench(0, 20000) for _ in range(2))            # G IMAD/s
@@ -340,6 +360,8 @@ def run_gpu(args):
                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                             "frac": gbs / hbm_peak, "traffic": traffic.get("k_combine", n)}}
     extra["hbm_peak_source"] = hbm_src
+    extra["msm_without_table"] = {"value": world * n / (plain_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": plain_ms,
+                                  "stage_ms": plain_stage, "note": "resident CRS, no precomputed window table"}
 
     # ---- CPU restatement of the reference's path on this box's host cores (rank 0, N = 1 only)
     cpu = None
@@ -368,7 +390,8 @@ def run_gpu(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (Montgomery Fq 12x32 / Fr 8x32)", "data": "synthetic",
             "config": {"workload": "share MSM G1, 2^%d points per GPU, uniform share scalars" % log_n,
-                       "points_per_gpu": n, "total_points": world * n, "sharding": "point range + NCCL all-gather of Jacobian partials",
+                       "points_per_gpu": n, "total_points": world * n,
+                       "crs": "registered on the device" + ("" if args.no_table else " with the 2^(22w)*P window table (one bucket set)"), "sharding": "point range + NCCL all-gather of Jacobian partials",
                        "l2": "inputs (%.1f GB of bases + scalars, %.1f GB of sort scratch) exceed the 126 MB L2" % (
                            n * 128 / 1e9, n * 16 * 8 / 1e9)},
             "stage_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
@@ -389,6 +412,7 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=20, help="log2 of the CPU baseline's sample")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-table", action="store_true", help="do not precompute the window table of the CRS")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -46,7 +46,7 @@ int32_t mpc_cuda_set_party(uint32_t party_id, uint32_t n_parties);
 int32_t mpc_cuda_set_device(int32_t dev_index);
 int32_t mpc_cuda_device_count(void);
 /* Tuning knobs for benchmarks and tests (process-wide; 0 restores the automatic choice):
- *   "msm_window_bits"  Pippenger window width c (3..16)
+ *   "msm_window_bits"  Pippenger window width c (3..23)
  *   "msm_task_len"     maximum points one accumulation task adds (bucket splitting)
  *   "profile"          1: bracket pipeline stages with CUDA events on the launching stream */
 int32_t mpc_cuda_set_option(const char* name, int64_t value);
@@ -146,6 +146,12 @@ int32_t mpc_cuda_msm_g1_register_bases(const uint64_t* bases_xy, const uint8_t* 
 int32_t mpc_cuda_msm_g1_register_bases_dev(const uint64_t* bases_xy_dev, size_t n, uint64_t* handle);
 int32_t mpc_cuda_msm_g2_register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle);
 int32_t mpc_cuda_msm_release_bases(uint64_t handle);
+/* Optional, once per registered CRS: build the table 2^(c*w) * P_i for every window w (c = window_bits,
+ * 0 = automatic; nwin x the size of the vector in HBM).  Later MSMs over the handle use one shared bucket
+ * set with c-bit windows: fewer mixed additions, one bucket reduction, no window doublings.  Results are
+ * the same group elements. */
+int32_t mpc_cuda_msm_g1_precompute(uint64_t handle, uint32_t window_bits);
+int32_t mpc_cuda_msm_g2_precompute(uint64_t handle, uint32_t window_bits);
 /* MSM over bases[offset .. offset+n) of a registered vector; scalars on the host */
 int32_t mpc_cuda_msm_g1_handle(uint64_t handle, size_t offset, const uint64_t* scalars_mont, size_t n,
                                uint64_t out_xy[12], uint8_t* out_inf);

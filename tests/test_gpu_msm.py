@@ -155,3 +155,37 @@ def test_g2_generate_and_handle(H, orc, pkg, g2bases):
     H.set_option("msm_task_len", 2)
     assert _same(H.msm_handle(h, sc), orc.g2_msm(g2bases, sc, threads=8))
     h.release()
+
+
+# ----------------------------------------------------------------------------- precomputed window tables
+@pytest.mark.parametrize("c", [0, 4, 9, 13, 16])
+def test_g1_precomputed_table(H, orc, pkg, bases8k, c):
+    infs = np.zeros(8192, dtype=np.uint8)
+    infs[[3, 4000]] = 1
+    h = H.register_bases(bases8k, inf=infs).precompute(c)
+    for seed, sc in ((1, pkg.synth.fr_uniform(0x1A0 + c, 8192)), (2, pkg.synth.fr_witness_like(0x1B0 + c, 8192))):
+        sc[:3] = P.fr_to_mont_arr([P.R_MOD - 1, 0, 1])
+        assert _same(H.msm_handle(h, sc), orc.g1_msm(bases8k, sc, inf=infs, threads=8))
+    sc = pkg.synth.fr_uniform(0x1C0, 777)
+    assert _same(H.msm_handle(h, sc, offset=5000), orc.g1_msm(bases8k[5000:5777], sc, inf=infs[5000:5777], threads=8))
+    h.release()
+
+
+def test_g1_precomputed_table_full_size_exact(H, orc, pkg):
+    log_n = 20
+    n = 1 << log_n
+    seed = pkg.synth.bench_seed(log_n)
+    dev = H.g1_generate(seed, n)
+    h = H.register_bases_dev(dev, n).precompute(0)
+    ks = helpers.gen_ks(pkg, seed, n)
+    for sc in (pkg.synth.fr_uniform(seed, n), pkg.synth.fr_witness_like(seed + 1, n)):
+        assert _same(H.msm_handle(h, sc), helpers.expected_msm_of_generated(orc, sc, ks))
+    h.release()
+    dev.free()
+
+
+def test_g2_precomputed_table(H, orc, pkg, g2bases):
+    h = H.register_bases(g2bases, g2=True).precompute(7)
+    sc = pkg.synth.fr_uniform(0x1D0, 600)
+    assert _same(H.msm_handle(h, sc), orc.g2_msm(g2bases, sc, threads=8))
+    h.release()

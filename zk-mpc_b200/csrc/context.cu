@@ -184,7 +184,7 @@ int32_t mpc_cuda_device_count(void) {
 int32_t mpc_cuda_set_option(const char* name, int64_t value) {
     MPC_ARG_CHECK(name != nullptr);
     if (!strcmp(name, "msm_window_bits")) {
-        MPC_ARG_CHECK(value >= 0 && value <= 16);
+        MPC_ARG_CHECK(value >= 0 && value <= 23);
         g_opt_msm_window_bits = value;
     } else if (!strcmp(name, "profile")) {
         g_opt_profile = value ? 1 : 0;

@@ -34,7 +34,7 @@ int64_t g_opt_msm_task_len = 0;
 
 namespace {
 
-constexpr uint32_t MAX_WINDOW_BITS = 16;       // 2^15 histogram bins x 4 B = 128 KB of shared memory
+constexpr uint32_t MAX_WINDOW_BITS = 23;       // bucket id <= 22 bits = 11 partition bits + 11 bin bits
 constexpr int ACC_THREADS = 128;
 constexpr int SORT_THREADS = 1024;
 constexpr uint32_t SMALL_MULTI_MAX = 64;
@@ -77,14 +77,23 @@ DEV void store_pod(T* p, const T& v) {
 
 // ---- plan -------------------------------------------------------------------------------------------
 struct Plan {
-    size_t n;
+    size_t n;                    // scalars of this call
+    size_t sn;                   // entries per sorted window: n, or nwin*n when all windows share one bucket set
+    uint32_t snwin;              // bucket sets: nwin, or 1 with a precomputed table of 2^(c*w)*P
     uint32_t c, nwin, nb;        // window bits, windows, buckets per window = 2^(c-1)
-    uint32_t chunks;             // sort chunks per window
+    uint32_t hi_bits, lo_bits;   // bucket id = (hi << lo_bits) | lo: level-1 partitions / level-2 bins
+    uint32_t chunks;             // level-1 sort chunks per window
     size_t chunk_len;
     uint32_t task_len;           // max points per accumulate task
     size_t max_tasks;
+    uint32_t scan_blocks;        // blocks of the task scan (SCAN_ITEMS buckets each)
     uint32_t red_m, red_t;       // bucket-reduce: red_t chunks of red_m buckets per window
+    uint32_t sum_parts;          // window-sum: first-level blocks per window
 };
+
+constexpr uint32_t HI_BITS_MAX = 11;            // <= 2048 write streams per CTA in the level-1 scatter
+constexpr uint32_t SCAN_PER_THREAD = 8;
+constexpr uint32_t SCAN_ITEMS = 1024 * SCAN_PER_THREAD;
 
 uint32_t log2_ceil(size_t x) {
     uint32_t l = 0;
@@ -92,28 +101,35 @@ uint32_t log2_ceil(size_t x) {
     return l;
 }
 
-Plan make_plan(size_t n, int sm_count) {
+Plan make_plan(size_t n, int sm_count, uint32_t table_c) {
     Plan p;
     p.n = n;
-    int64_t c = g_opt_msm_window_bits;
+    int64_t c = table_c ? table_c : g_opt_msm_window_bits;
     if (c <= 0) {
-        // madds = n * windows, bucket work ~ windows * 2^(c-1): c ~ log2(n) - 4 balances them on this part
+        // madds = n * windows against bucket work ~ windows * 2^(c-1) * 3; measured on B200 with
+        // tools/tune_msm.py (2^24: c = 20, 2^20: c = 17, 2^16: c = 15).  Widths whose top window holds a
+        // single bit (253 mod c == 1) are skipped: they put half of a window's entries in one bucket.
         int l = (int)log2_ceil(n);
-        c = l - 4;
+        c = l >= 23 ? 20 : l >= 21 ? 19 : l >= 19 ? 17 : l >= 17 ? 16 : l >= 14 ? 15 : l >= 11 ? 11 : l >= 8 ? 8 : 4;
     }
     if (c < 3) c = 3;
     if (c > MAX_WINDOW_BITS) c = MAX_WINDOW_BITS;
     p.c = (uint32_t)c;
     p.nwin = msm::num_windows(p.c);
     p.nb = 1u << (p.c - 1);
-    uint32_t want = (uint32_t)((2 * sm_count + p.nwin - 1) / p.nwin);
-    size_t by_len = (n + 4095) / 4096;
+    uint32_t kb = p.c - 1;
+    p.hi_bits = kb < HI_BITS_MAX ? kb : HI_BITS_MAX;
+    p.lo_bits = kb - p.hi_bits;
+    p.snwin = table_c ? 1 : p.nwin;
+    p.sn = table_c ? n * p.nwin : n;
+    uint32_t want = (uint32_t)((4 * sm_count + p.snwin - 1) / p.snwin);
+    size_t by_len = (p.sn + 8191) / 8192;
     p.chunks = (uint32_t)(by_len < want ? by_len : want);
     if (p.chunks < 1) p.chunks = 1;
-    p.chunk_len = (n + p.chunks - 1) / p.chunks;
+    p.chunk_len = (p.sn + p.chunks - 1) / p.chunks;
     int64_t tl = g_opt_msm_task_len;
     if (tl <= 0) {
-        // enough tasks to balance ~4 rounds over the resident threads, but not so short that joins dominate
+        // enough tasks to balance the resident threads, but not so short that joins dominate
         size_t entries = n * (size_t)p.nwin;
         size_t resident = (size_t)sm_count * 384;
         tl = (int64_t)(entries / (resident * 8));
@@ -121,9 +137,12 @@ Plan make_plan(size_t n, int sm_count) {
         if (tl > 256) tl = 256;
     }
     p.task_len = (uint32_t)tl;
-    p.max_tasks = n * (size_t)p.nwin / p.task_len + (size_t)p.nwin * p.nb + 1;
-    p.red_m = p.nb < 32 ? p.nb : 32;
+    size_t nbuckets = (size_t)p.snwin * p.nb;
+    p.max_tasks = n * (size_t)p.nwin / p.task_len + nbuckets + 1;
+    p.scan_blocks = (uint32_t)((nbuckets + SCAN_ITEMS - 1) / SCAN_ITEMS);
+    p.red_m = p.nb < 32 ? p.nb : (p.nb > (1u << 16) ? 64 : 32);
     p.red_t = p.nb / p.red_m;
+    p.sum_parts = (p.red_t + 1023) / 1024;       // <= 1024 chunk results per first-level block
     return p;
 }
 
@@ -140,23 +159,6 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
             digits[(size_t)w * n + i] = skip ? 0u : d;
         }
     }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) k_hist(const uint32_t* __restrict__ digits, size_t n, uint32_t nb,
-                                                       size_t chunk_len, uint32_t* __restrict__ hist) {
-    extern __shared__ uint32_t sm[];
-    uint32_t w = blockIdx.y, ch = blockIdx.x;
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) sm[b] = 0;
-    __syncthreads();
-    size_t lo = (size_t)ch * chunk_len, hi = lo + chunk_len < n ? lo + chunk_len : n;
-    const uint32_t* d = digits + (size_t)w * n;
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        uint32_t m = d[i] & ~msm::DIGIT_NEG;
-        if (m) atomicAdd(&sm[m - 1], 1u);
-    }
-    __syncthreads();
-    uint32_t* out = hist + ((size_t)w * gridDim.x + ch) * nb;
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) out[b] = sm[b];
 }
 
 // exclusive scan of one value per thread across the block; returns the thread's prefix, *total = block sum
@@ -176,89 +178,219 @@ DEV uint32_t block_exclusive_scan(uint32_t v, uint32_t* sm /* blockDim.x */, uin
     return incl - v;
 }
 
-// one block per window: bucket sizes / start offsets, and hist[w][chunk][b] -> first slot of that chunk
-__global__ void __launch_bounds__(1024) k_scan_window(uint32_t* __restrict__ hist, uint32_t chunks, uint32_t nb,
-                                                      uint32_t* __restrict__ bucket_start,
-                                                      uint32_t* __restrict__ bucket_size) {
+// Two-level counting sort of the (window, point) entries by bucket id = digit magnitude - 1.
+// Level 1 partitions each window by the low 11 bits of the bucket id (<= 2048 partitions, so a CTA keeps
+// few open write streams and its 8-byte stores merge into full sectors in L2); level 2 finishes every
+// partition inside one CTA by the remaining high bits, where it also derives the bucket start / size
+// tables (a bucket's run may sit anywhere in the window's list; only (start, size) matter).
+// The order inside a bucket is arbitrary (atomics), which is fine: group addition commutes.
+
+// level 1a: per (window, chunk) histogram of the partition id
+__global__ void __launch_bounds__(SORT_THREADS) k_hist1(const uint32_t* __restrict__ digits, size_t n,
+                                                        uint32_t lo_bits, uint32_t hbins, size_t chunk_len,
+                                                        uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t sm[];
+    uint32_t w = blockIdx.y, ch = blockIdx.x;
+    for (uint32_t b = threadIdx.x; b < hbins; b += blockDim.x) sm[b] = 0;
+    __syncthreads();
+    size_t lo = (size_t)ch * chunk_len, hi = lo + chunk_len < n ? lo + chunk_len : n;
+    const uint32_t* d = digits + (size_t)w * n;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        uint32_t m = d[i] & ~msm::DIGIT_NEG;
+        if (m) atomicAdd(&sm[(m - 1) & (hbins - 1)], 1u);
+    }
+    __syncthreads();
+    uint32_t* out = hist + ((size_t)w * gridDim.x + ch) * hbins;
+    for (uint32_t b = threadIdx.x; b < hbins; b += blockDim.x) out[b] = sm[b];
+}
+
+// level 1b: one block per window: partition starts, and hist[w][chunk][p] -> first slot of that chunk
+__global__ void __launch_bounds__(1024) k_scan1(uint32_t* __restrict__ hist, uint32_t chunks, uint32_t hbins,
+                                                uint32_t* __restrict__ part_start /* [nwin][hbins + 1] */) {
     __shared__ uint32_t sm[1024];
     uint32_t w = blockIdx.x;
-    uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
-    uint32_t b0 = threadIdx.x * per, b1 = b0 + per < nb ? b0 + per : nb;
-    uint32_t* h = hist + (size_t)w * chunks * nb;
+    uint32_t per = (hbins + blockDim.x - 1) / blockDim.x;
+    uint32_t b0 = threadIdx.x * per, b1 = b0 + per < hbins ? b0 + per : hbins;
+    if (b0 > hbins) b0 = hbins;
+    uint32_t* h = hist + (size_t)w * chunks * hbins;
     uint32_t tot = 0;
+    for (uint32_t b = b0; b < b1; b++)
+        for (uint32_t ch = 0; ch < chunks; ch++) tot += h[(size_t)ch * hbins + b];
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(tot, sm, &total);
     for (uint32_t b = b0; b < b1; b++) {
-        uint32_t s = 0;
-        for (uint32_t ch = 0; ch < chunks; ch++) s += h[(size_t)ch * nb + b];
-        bucket_size[(size_t)w * nb + b] = s;
-        tot += s;
-    }
-    uint32_t run = block_exclusive_scan(tot, sm, nullptr);
-    for (uint32_t b = b0; b < b1; b++) {
-        bucket_start[(size_t)w * nb + b] = run;
+        part_start[(size_t)w * (hbins + 1) + b] = run;
         for (uint32_t ch = 0; ch < chunks; ch++) {
-            uint32_t t = h[(size_t)ch * nb + b];
-            h[(size_t)ch * nb + b] = run;
+            uint32_t t = h[(size_t)ch * hbins + b];
+            h[(size_t)ch * hbins + b] = run;
             run += t;
+        }
+    }
+    if (threadIdx.x == 0) part_start[(size_t)w * (hbins + 1) + hbins] = total;
+}
+
+// level 1c: scatter (point index | sign, low bucket bits) pairs into their partition
+__global__ void __launch_bounds__(SORT_THREADS) k_scatter1(const uint32_t* __restrict__ digits, size_t n,
+                                                           uint32_t lo_bits, uint32_t hbins, size_t chunk_len,
+                                                           const uint32_t* __restrict__ cursors,
+                                                           uint2* __restrict__ pairs, size_t inner, size_t stride,
+                                                           size_t offset) {
+    extern __shared__ uint32_t sm[];
+    uint32_t w = blockIdx.y, ch = blockIdx.x;
+    const uint32_t* cur = cursors + ((size_t)w * gridDim.x + ch) * hbins;
+    for (uint32_t b = threadIdx.x; b < hbins; b += blockDim.x) sm[b] = cur[b];
+    __syncthreads();
+    size_t lo = (size_t)ch * chunk_len, hi = lo + chunk_len < n ? lo + chunk_len : n;
+    const uint32_t* d = digits + (size_t)w * n;
+    uint2* out = pairs + (size_t)w * n;
+    const uint32_t hi_bits = 31 - __clz(hbins);
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        uint32_t e = d[i], m = e & ~msm::DIGIT_NEG;
+        if (m) {
+            uint32_t key = m - 1;
+            uint32_t pos = atomicAdd(&sm[key & (hbins - 1)], 1u);
+            // point index: i itself, or (window, point) -> row of the precomputed table [nwin][stride]
+            uint32_t pt = stride ? (uint32_t)((i / inner) * stride + offset + i % inner) : (uint32_t)i;
+            out[pos] = make_uint2(pt | (e & msm::DIGIT_NEG), key >> hi_bits);
         }
     }
 }
 
-// single block: exclusive scan of ceil(size / task_len) over all buckets; counters[0] = total tasks
-__global__ void __launch_bounds__(1024) k_task_scan(const uint32_t* __restrict__ bucket_size, size_t nbuckets,
-                                                    uint32_t task_len, uint32_t* __restrict__ task_start,
-                                                    uint32_t* __restrict__ counters) {
-    __shared__ uint32_t sm[1024];
-    size_t per = (nbuckets + blockDim.x - 1) / blockDim.x;
-    size_t g0 = threadIdx.x * per, g1 = g0 + per < nbuckets ? g0 + per : nbuckets;
+// level 2: one CTA per (partition, window): histogram of the low bits, bucket tables, final scatter.
+// A partition can be huge (tiny top window: every entry of the window shares 2-3 buckets; 0/1-heavy
+// scalars), so the CTA is wide (1024 threads) and keeps SORT2_ILP independent loads in flight per
+// thread, and shared atomics are warp-aggregated so a hot counter is hit once per warp.
+constexpr int SORT2_THREADS = 1024;
+constexpr int SORT2_ILP = 4;
+
+__global__ void __launch_bounds__(SORT2_THREADS) k_sort2(const uint2* __restrict__ pairs,
+                                                         const uint32_t* __restrict__ part_start, size_t n,
+                                                         uint32_t lo_bits, uint32_t hbins, uint32_t* __restrict__ sorted,
+                                                         uint32_t* __restrict__ bucket_start,
+                                                         uint32_t* __restrict__ bucket_size) {
+    extern __shared__ uint32_t sm[];            // lbins counters, then blockDim.x scan slots
+    const uint32_t lbins = 1u << lo_bits;
+    uint32_t* cnt = sm;
+    uint32_t* scan = sm + lbins;
+    uint32_t w = blockIdx.y, p = blockIdx.x;
+    uint32_t lo = part_start[(size_t)w * (hbins + 1) + p], hi = part_start[(size_t)w * (hbins + 1) + p + 1];
+    const uint2* in = pairs + (size_t)w * n;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t step = blockDim.x * SORT2_ILP;
+    for (uint32_t b = threadIdx.x; b < lbins; b += blockDim.x) cnt[b] = 0;
+    __syncthreads();
+    for (uint32_t i0 = lo; i0 < hi; i0 += step) {
+        uint32_t key[SORT2_ILP];
+#pragma unroll
+        for (int u = 0; u < SORT2_ILP; u++) {
+            uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+            key[u] = i < hi ? in[i].y : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < SORT2_ILP; u++) {
+            uint32_t peers = __match_any_sync(0xffffffffu, key[u]);
+            if (key[u] != 0xffffffffu && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&cnt[key[u]], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    uint32_t per = (lbins + blockDim.x - 1) / blockDim.x;
+    uint32_t b0 = threadIdx.x * per, b1 = b0 + per < lbins ? b0 + per : lbins;
+    if (b0 > lbins) b0 = lbins;
     uint32_t tot = 0;
-    for (size_t g = g0; g < g1; g++) tot += (bucket_size[g] + task_len - 1) / task_len;
+    for (uint32_t b = b0; b < b1; b++) tot += cnt[b];
+    uint32_t run = lo + block_exclusive_scan(tot, scan, nullptr);
+    // bucket id = (bin << hi_bits) | partition: level 1 splits on the LOW bits of the bucket id, which
+    // stay well spread when the digits are skewed towards small values (top window, small scalars)
+    const uint32_t hi_bits = 31 - __clz(hbins);
+    size_t g0 = ((size_t)w << (lo_bits + hi_bits)) + p;
+    for (uint32_t b = b0; b < b1; b++) {
+        uint32_t t = cnt[b];
+        bucket_start[g0 + ((size_t)b << hi_bits)] = run;
+        bucket_size[g0 + ((size_t)b << hi_bits)] = t;
+        cnt[b] = run;
+        run += t;
+    }
+    __syncthreads();
+    uint32_t* out = sorted + (size_t)w * n;
+    for (uint32_t i0 = lo; i0 < hi; i0 += step) {
+        uint2 e[SORT2_ILP];
+#pragma unroll
+        for (int u = 0; u < SORT2_ILP; u++) {
+            uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+            e[u] = i < hi ? in[i] : make_uint2(0, 0xffffffffu);
+        }
+#pragma unroll
+        for (int u = 0; u < SORT2_ILP; u++) {
+            uint32_t peers = __match_any_sync(0xffffffffu, e[u].y);
+            uint32_t leader = (uint32_t)(__ffs(peers) - 1), base = 0;
+            if (e[u].y != 0xffffffffu && lane == leader) base = atomicAdd(&cnt[e[u].y], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (e[u].y != 0xffffffffu) out[base + __popc(peers & ((1u << lane) - 1u))] = e[u].x;
+        }
+    }
+}
+
+// ---- task table: cut buckets into runs of <= task_len entries ------------------------------------------
+// (a) per-block totals of ceil(size / task_len)
+__global__ void __launch_bounds__(1024) k_task_sums(const uint32_t* __restrict__ bucket_size, size_t nbuckets,
+                                                    uint32_t task_len, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t sm[1024];
+    size_t g0 = ((size_t)blockIdx.x * 1024 + threadIdx.x) * SCAN_PER_THREAD;
+    uint32_t tot = 0;
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++)
+        if (g0 + k < nbuckets) tot += (bucket_size[g0 + k] + task_len - 1) / task_len;
+    uint32_t total;
+    block_exclusive_scan(tot, sm, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// (b) single block: exclusive scan of the block totals in place; counters[0] = number of tasks
+__global__ void __launch_bounds__(1024) k_task_offsets(uint32_t* __restrict__ block_sums, uint32_t nblocks,
+                                                       uint32_t* __restrict__ counters) {
+    __shared__ uint32_t sm[1024];
+    uint32_t per = (nblocks + blockDim.x - 1) / blockDim.x;
+    uint32_t b0 = threadIdx.x * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+    if (b0 > nblocks) b0 = nblocks;
+    uint32_t tot = 0;
+    for (uint32_t b = b0; b < b1; b++) tot += block_sums[b];
     uint32_t total;
     uint32_t run = block_exclusive_scan(tot, sm, &total);
-    for (size_t g = g0; g < g1; g++) {
-        task_start[g] = run;
-        run += (bucket_size[g] + task_len - 1) / task_len;
+    for (uint32_t b = b0; b < b1; b++) {
+        uint32_t t = block_sums[b];
+        block_sums[b] = run;
+        run += t;
     }
     if (threadIdx.x == 0) counters[0] = total;
 }
 
-// task = (first slot in the window's sorted list, length, bucket, bucket-has-a-single-task)
-__global__ void __launch_bounds__(256) k_build_tasks(const uint32_t* __restrict__ bucket_start,
-                                                     const uint32_t* __restrict__ bucket_size,
-                                                     const uint32_t* __restrict__ task_start, size_t nbuckets,
-                                                     uint32_t task_len, uint4* __restrict__ tasks,
-                                                     uint32_t* __restrict__ small_list, uint32_t* __restrict__ big_list,
-                                                     uint32_t* __restrict__ counters) {
-    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nbuckets) return;
-    uint32_t size = bucket_size[g];
-    if (size == 0) return;
-    uint32_t nt = (size + task_len - 1) / task_len, ts = task_start[g], pos = bucket_start[g];
-    for (uint32_t k = 0; k < nt; k++) {
-        uint32_t len = size - k * task_len < task_len ? size - k * task_len : task_len;
-        tasks[ts + k] = make_uint4(pos + k * task_len, len, (uint32_t)g, nt == 1 ? 1u : 0u);
-    }
-    if (nt > 1) {
-        if (nt <= SMALL_MULTI_MAX) small_list[atomicAdd(&counters[2], 1u)] = (uint32_t)g;
-        else big_list[atomicAdd(&counters[3], 1u)] = (uint32_t)g;
-    }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __restrict__ digits, size_t n, uint32_t nb,
-                                                          size_t chunk_len, const uint32_t* __restrict__ cursors,
-                                                          uint32_t* __restrict__ sorted) {
-    extern __shared__ uint32_t sm[];
-    uint32_t w = blockIdx.y, ch = blockIdx.x;
-    const uint32_t* cur = cursors + ((size_t)w * gridDim.x + ch) * nb;
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) sm[b] = cur[b];
-    __syncthreads();
-    size_t lo = (size_t)ch * chunk_len, hi = lo + chunk_len < n ? lo + chunk_len : n;
-    const uint32_t* d = digits + (size_t)w * n;
-    uint32_t* out = sorted + (size_t)w * n;
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        uint32_t e = d[i], m = e & ~msm::DIGIT_NEG;
-        if (m) {
-            uint32_t pos = atomicAdd(&sm[m - 1], 1u);
-            out[pos] = (uint32_t)i | (e & msm::DIGIT_NEG);
+// (c) task = (first slot in the window's sorted list, length, bucket, bucket-has-a-single-task)
+__global__ void __launch_bounds__(1024) k_build_tasks(const uint32_t* __restrict__ bucket_start,
+                                                      const uint32_t* __restrict__ bucket_size,
+                                                      const uint32_t* __restrict__ block_offs, size_t nbuckets,
+                                                      uint32_t task_len, uint4* __restrict__ tasks,
+                                                      uint32_t* __restrict__ task_start,
+                                                      uint32_t* __restrict__ small_list, uint32_t* __restrict__ big_list,
+                                                      uint32_t* __restrict__ counters) {
+    __shared__ uint32_t sm[1024];
+    size_t g0 = ((size_t)blockIdx.x * 1024 + threadIdx.x) * SCAN_PER_THREAD;
+    uint32_t tot = 0;
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++)
+        if (g0 + k < nbuckets) tot += (bucket_size[g0 + k] + task_len - 1) / task_len;
+    uint32_t ts = block_offs[blockIdx.x] + block_exclusive_scan(tot, sm, nullptr);
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) {
+        size_t g = g0 + k;
+        if (g >= nbuckets) break;
+        uint32_t size = bucket_size[g];
+        uint32_t nt = (size + task_len - 1) / task_len, pos = bucket_start[g];
+        task_start[g] = ts;
+        for (uint32_t j = 0; j < nt; j++) {
+            uint32_t len = size - j * task_len < task_len ? size - j * task_len : task_len;
+            tasks[ts + j] = make_uint4(pos + j * task_len, len, (uint32_t)g, nt == 1 ? 1u : 0u);
+        }
+        ts += nt;
+        if (nt > 1) {
+            if (nt <= SMALL_MULTI_MAX) small_list[atomicAdd(&counters[2], 1u)] = (uint32_t)g;
+            else big_list[atomicAdd(&counters[3], 1u)] = (uint32_t)g;
         }
     }
 }
@@ -380,16 +512,17 @@ __global__ void __launch_bounds__(ACC_THREADS) k_bucket_reduce(const XYZZ<F>* __
     store_pod(chunk_res + id, acc);
 }
 
-// one block per window: sum of its T chunk results
+// block (part, w) sums items [part*len, (part+1)*len) of window w's `count` inputs -> out[w*parts + part]
 template <class F>
-__global__ void __launch_bounds__(ACC_THREADS) k_window_sum(const XYZZ<F>* __restrict__ chunk_res, uint32_t T,
-                                                            XYZZ<F>* __restrict__ window_sum) {
+__global__ void __launch_bounds__(ACC_THREADS) k_window_sum(const XYZZ<F>* __restrict__ in, uint32_t count,
+                                                            uint32_t len, XYZZ<F>* __restrict__ out) {
     extern __shared__ uint4 sm_raw[];
     XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(sm_raw);
-    uint32_t w = blockIdx.x;
+    uint32_t w = blockIdx.y, part = blockIdx.x;
+    uint32_t lo = part * len, hi = lo + len < count ? lo + len : count;
     XYZZ<F> acc = XYZZ<F>::infinity();
-    for (uint32_t k = threadIdx.x; k < T; k += blockDim.x) {
-        XYZZ<F> q = load_pod(chunk_res + (size_t)w * T + k);
+    for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+        XYZZ<F> q = load_pod(in + (size_t)w * count + k);
         xyzz_add(acc, q);
     }
     store_pod(sm + threadIdx.x, acc);
@@ -404,7 +537,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_window_sum(const XYZZ<F>* __res
     }
     if (threadIdx.x == 0) {
         XYZZ<F> a = load_pod(sm);
-        store_pod(window_sum + w, a);
+        store_pod(out + (size_t)w * gridDim.x + part, a);
     }
 }
 
@@ -490,72 +623,96 @@ int32_t allow_smem(K kernel, size_t bytes) {
     return MPC_CUDA_OK;
 }
 
+// A registered base vector may carry a table T[w][i] = 2^(c*w) * P_i (affine).  Then every window adds
+// into ONE shared bucket set (Σ_w 2^(cw) d_w P = Σ_w d_w T[w]), the bucket reduction runs once instead of
+// per window and the Horner doublings disappear, which makes wide windows (c = 22) pay: ~25 % fewer
+// mixed additions at n = 2^24.  180 GB of HBM is what makes a 12x CRS copy affordable.
+struct TableRef {
+    const void* table = nullptr;   // Affine<F>[nwin][stride]
+    uint32_t c = 0;
+    size_t stride = 0, offset = 0;
+};
+
 // result (one XYZZ on the device) = Σ scalars[i] * bases[i]
 template <class F>
 int32_t msm_run(const Affine<F>* bases, const uint8_t* inf, const Fr* scalars, size_t n, XYZZ<F>* result,
-                cudaStream_t s) {
+                cudaStream_t s, const TableRef* tbl = nullptr) {
     if (n == 0) {
         MPC_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(XYZZ<F>), s));
         return MPC_CUDA_OK;
     }
     MPC_ARG_CHECK(n < ((size_t)1 << 31));
     const DeviceInfo* dev = current_device_info();
-    Plan p = make_plan(n, dev->sm_count);
-    size_t nbuckets = (size_t)p.nwin * p.nb;
+    const bool use_table = tbl && tbl->table;
+    Plan p = make_plan(n, dev->sm_count, use_table ? tbl->c : 0);
+    const size_t sn = p.sn;
+    const uint32_t snwin = p.snwin;
+    size_t nbuckets = (size_t)snwin * p.nb;
+    MPC_ARG_CHECK(sn < ((size_t)1 << 31) && (!use_table || (size_t)p.nwin * tbl->stride < ((size_t)1 << 31)));
     MPC_ARG_CHECK(nbuckets < ((size_t)1 << 31) && (size_t)p.nwin * n / p.task_len + nbuckets < ((size_t)1 << 32));
 
-    Scratch s_digits, s_sorted, s_hist, s_bstart, s_bsize, s_tstart, s_tasks, s_small, s_big, s_cnt, s_buckets,
-        s_partials, s_chunk, s_wsum;
-    uint32_t *digits, *sorted, *hist, *bstart, *bsize, *tstart, *small_list, *big_list, *counters;
+    Scratch s_digits, s_sorted, s_pairs, s_hist, s_part, s_bstart, s_bsize, s_tstart, s_bsums, s_tasks, s_small, s_big,
+        s_cnt, s_buckets, s_partials, s_chunk, s_wpart, s_wsum;
+    uint32_t *digits, *sorted, *hist, *part_start, *bstart, *bsize, *tstart, *bsums, *small_list, *big_list, *counters;
+    uint2* pairs;
     uint4* tasks;
-    XYZZ<F>*buckets, *partials, *chunk_res, *wsum;
+    XYZZ<F>*buckets, *partials, *chunk_res, *wpart, *wsum;
+    const uint32_t hbins = 1u << p.hi_bits, lbins = 1u << p.lo_bits;
     MPC_TRY(s_digits.alloc(&digits, (size_t)p.nwin * n, s));
     MPC_TRY(s_sorted.alloc(&sorted, (size_t)p.nwin * n, s));
-    MPC_TRY(s_hist.alloc(&hist, (size_t)p.nwin * p.chunks * p.nb, s));
+    MPC_TRY(s_pairs.alloc(&pairs, (size_t)p.nwin * n, s));
+    MPC_TRY(s_hist.alloc(&hist, (size_t)snwin * p.chunks * hbins, s));
+    MPC_TRY(s_part.alloc(&part_start, (size_t)snwin * (hbins + 1), s));
     MPC_TRY(s_bstart.alloc(&bstart, nbuckets, s));
     MPC_TRY(s_bsize.alloc(&bsize, nbuckets, s));
     MPC_TRY(s_tstart.alloc(&tstart, nbuckets, s));
+    MPC_TRY(s_bsums.alloc(&bsums, p.scan_blocks, s));
     MPC_TRY(s_tasks.alloc(&tasks, p.max_tasks, s));
     MPC_TRY(s_small.alloc(&small_list, nbuckets, s));
     MPC_TRY(s_big.alloc(&big_list, nbuckets, s));
     MPC_TRY(s_cnt.alloc(&counters, 8, s));
     MPC_TRY(s_buckets.alloc(&buckets, nbuckets, s));
     MPC_TRY(s_partials.alloc(&partials, p.max_tasks, s));
-    MPC_TRY(s_chunk.alloc(&chunk_res, (size_t)p.nwin * p.red_t, s));
-    MPC_TRY(s_wsum.alloc(&wsum, p.nwin, s));
+    MPC_TRY(s_chunk.alloc(&chunk_res, (size_t)snwin * p.red_t, s));
+    MPC_TRY(s_wpart.alloc(&wpart, (size_t)snwin * p.sum_parts, s));
+    MPC_TRY(s_wsum.alloc(&wsum, snwin, s));
 
     ProfileScope prof_total("msm_total", s);
     profile_begin("msm_sort", s);
     MPC_CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(uint32_t), s));
     MPC_CUDA_TRY(cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), s));      // all-zero = infinity
 
+    // digits[w*n + i]: with a table the flat array IS one window of nwin*n entries
     k_digits<<<grid_for(n, 256, 8), 256, 0, s>>>(scalars, inf, n, p.c, p.nwin, digits);
     MPC_KERNEL_CHECK();
 
-    size_t sort_smem = (size_t)p.nb * sizeof(uint32_t);
-    MPC_TRY(allow_smem(k_hist, sort_smem));
-    MPC_TRY(allow_smem(k_scatter, sort_smem));
-    dim3 sort_grid(p.chunks, p.nwin);
-    k_hist<<<sort_grid, SORT_THREADS, sort_smem, s>>>(digits, n, p.nb, p.chunk_len, hist);
+    dim3 grid1(p.chunks, snwin);
+    k_hist1<<<grid1, SORT_THREADS, hbins * sizeof(uint32_t), s>>>(digits, sn, p.lo_bits, hbins, p.chunk_len, hist);
     MPC_KERNEL_CHECK();
-    k_scan_window<<<p.nwin, 1024, 0, s>>>(hist, p.chunks, p.nb, bstart, bsize);
+    k_scan1<<<snwin, 1024, 0, s>>>(hist, p.chunks, hbins, part_start);
     MPC_KERNEL_CHECK();
-    k_task_scan<<<1, 1024, 0, s>>>(bsize, nbuckets, p.task_len, tstart, counters);
+    k_scatter1<<<grid1, SORT_THREADS, hbins * sizeof(uint32_t), s>>>(digits, sn, p.lo_bits, hbins, p.chunk_len, hist, pairs,
+                                                                    n, use_table ? tbl->stride : 0,
+                                                                    use_table ? tbl->offset : 0);
     MPC_KERNEL_CHECK();
-    k_build_tasks<<<(unsigned)((nbuckets + 255) / 256), 256, 0, s>>>(bstart, bsize, tstart, nbuckets, p.task_len, tasks,
-                                                                    small_list, big_list, counters);
+    k_sort2<<<dim3(hbins, snwin), SORT2_THREADS, (lbins + SORT2_THREADS) * sizeof(uint32_t), s>>>(pairs, part_start, sn, p.lo_bits, hbins, sorted,
+                                                                             bstart, bsize);
     MPC_KERNEL_CHECK();
-    k_scatter<<<sort_grid, SORT_THREADS, sort_smem, s>>>(digits, n, p.nb, p.chunk_len, hist, sorted);
+    k_task_sums<<<p.scan_blocks, 1024, 0, s>>>(bsize, nbuckets, p.task_len, bsums);
     MPC_KERNEL_CHECK();
-
+    k_task_offsets<<<1, 1024, 0, s>>>(bsums, p.scan_blocks, counters);
+    MPC_KERNEL_CHECK();
+    k_build_tasks<<<p.scan_blocks, 1024, 0, s>>>(bstart, bsize, bsums, nbuckets, p.task_len, tasks, tstart, small_list,
+                                                 big_list, counters);
+    MPC_KERNEL_CHECK();
     profile_end("msm_sort", s);
 
     int acc_blocks = 0;
     MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F>, ACC_THREADS, 0));
     if (acc_blocks < 1) acc_blocks = 1;
     profile_begin("msm_accumulate", s);
-    k_accumulate<F><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(bases, sorted, n, p.nb, tasks, counters, buckets,
-                                                                      partials);
+    k_accumulate<F><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(
+        use_table ? (const Affine<F>*)tbl->table : bases, sorted, sn, p.nb, tasks, counters, buckets, partials);
     MPC_KERNEL_CHECK();
     profile_end("msm_accumulate", s);
     profile_begin("msm_reduce", s);
@@ -570,13 +727,15 @@ int32_t msm_run(const Affine<F>* bases, const uint8_t* inf, const Fr* scalars, s
                                                                     partials, buckets);
     MPC_KERNEL_CHECK();
 
-    uint32_t red_threads = p.nwin * p.red_t;
-    k_bucket_reduce<F><<<(red_threads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(buckets, p.nwin, p.nb,
+    uint32_t red_threads = snwin * p.red_t;
+    k_bucket_reduce<F><<<(red_threads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(buckets, snwin, p.nb,
                                                                                             p.red_m, p.red_t, chunk_res);
     MPC_KERNEL_CHECK();
-    k_window_sum<F><<<p.nwin, ACC_THREADS, tree_smem, s>>>(chunk_res, p.red_t, wsum);
+    k_window_sum<F><<<dim3(p.sum_parts, snwin), ACC_THREADS, tree_smem, s>>>(chunk_res, p.red_t, 1024, wpart);
     MPC_KERNEL_CHECK();
-    k_horner<F><<<1, 32, 0, s>>>(wsum, p.nwin, p.c, result);
+    k_window_sum<F><<<dim3(1, snwin), ACC_THREADS, tree_smem, s>>>(wpart, p.sum_parts, p.sum_parts, wsum);
+    MPC_KERNEL_CHECK();
+    k_horner<F><<<1, 32, 0, s>>>(wsum, snwin, p.c, result);
     MPC_KERNEL_CHECK();
     profile_end("msm_reduce", s);
     return MPC_CUDA_OK;
@@ -590,6 +749,8 @@ struct BaseVec {
     int cuda_device = 0;
     bool g2 = false;
     bool owned = true;
+    void* table = nullptr;       // Affine<F>[nwin(table_c)][n]: 2^(table_c*w) * P_i, or nullptr
+    uint32_t table_c = 0;
 };
 std::mutex g_bases_mu;
 std::unordered_map<uint64_t, BaseVec> g_bases;
@@ -641,15 +802,89 @@ int32_t find_bases(uint64_t handle, bool g2, size_t offset, size_t n, BaseVec* o
     return MPC_CUDA_OK;
 }
 
+TableRef table_of(const BaseVec& v, size_t offset) {
+    TableRef t;
+    t.table = v.table;
+    t.c = v.table_c;
+    t.stride = v.n;
+    t.offset = offset;
+    return t;
+}
+
+// T[w][i] = 2^(c*w) * P_i in affine form, one thread per base (c doublings per window, one inversion per
+// entry; run once per registered CRS)
+template <class F>
+__global__ void __launch_bounds__(ACC_THREADS) k_precompute(const Affine<F>* __restrict__ bases,
+                                                            const uint8_t* __restrict__ inf, size_t n, uint32_t c,
+                                                            uint32_t nwin, Affine<F>* __restrict__ table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> pt = load_pod_ro(bases + i);
+    store_pod(table + i, pt);
+    if (inf && inf[i]) return;                 // never referenced: its digits are zero
+    XYZZ<F> acc;
+    acc.x = pt.x; acc.y = pt.y; acc.zz = F::one(); acc.zzz = F::one();
+    for (uint32_t w = 1; w < nwin; w++) {
+        for (uint32_t k = 0; k < c; k++) xyzz_dbl(acc);
+        Affine<F> r;
+        xyzz_to_affine(acc, r.x, r.y);
+        store_pod(table + (size_t)w * n + i, r);
+        acc.x = r.x; acc.y = r.y; acc.zz = F::one(); acc.zzz = F::one();
+    }
+}
+
+template <class F>
+int32_t precompute(uint64_t handle, uint32_t window_bits, bool g2) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_ARG_CHECK(window_bits == 0 || (window_bits >= 3 && window_bits <= MAX_WINDOW_BITS));
+    BaseVec v;
+    MPC_TRY(find_bases(handle, g2, 0, 0, &v));
+    uint32_t c = window_bits;
+    if (c == 0) {
+        uint32_t l = log2_ceil(v.n ? v.n : 1);
+        c = l >= 23 ? 23 : l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 15 : l > 7 ? l - 3 : 4;
+        if (msm::SCALAR_BITS % c == 1) c--;       // a one-bit top window would put n/2 entries in one bucket
+    }
+    uint32_t nwin = msm::num_windows(c);
+    MPC_ARG_CHECK((size_t)nwin * v.n < ((size_t)1 << 31));
+    void* table = nullptr;
+    MPC_CUDA_TRY(cudaMalloc(&table, (size_t)nwin * (v.n ? v.n : 1) * sizeof(Affine<F>)));
+    if (v.n) {
+        k_precompute<F><<<(unsigned)((v.n + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, s>>>(
+            (const Affine<F>*)v.bases, v.inf, v.n, c, nwin, (Affine<F>*)table);
+        MPC_KERNEL_CHECK();
+    }
+    MPC_CUDA_TRY(cudaStreamSynchronize(s));
+    void* old = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_bases_mu);
+        auto it = g_bases.find(handle);
+        if (it == g_bases.end()) {
+            cudaFree(table);
+            set_error("base handle %llu released during precomputation", (unsigned long long)handle);
+            return MPC_CUDA_ERR_HANDLE;
+        }
+        old = it->second.table;
+        it->second.table = table;
+        it->second.table_c = c;
+    }
+    if (old) {
+        MPC_CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(old);
+    }
+    return MPC_CUDA_OK;
+}
+
 // run + emit; scalars already on the device.  host_out: affine limbs + flag copied back and synchronised.
 template <class F>
 int32_t msm_emit(const Affine<F>* bases, const uint8_t* inf, const Fr* scalars_dev, size_t n, uint32_t mode,
-                 uint32_t* out_dev, uint64_t* host_xy, uint8_t* host_inf, cudaStream_t s) {
+                 uint32_t* out_dev, uint64_t* host_xy, uint8_t* host_inf, cudaStream_t s, const TableRef* tbl = nullptr) {
     constexpr int N = sizeof(F) / 4;
     Scratch s_res, s_out;
     XYZZ<F>* res;
     MPC_TRY(s_res.alloc(&res, 1, s));
-    MPC_TRY(msm_run<F>(bases, inf, scalars_dev, n, res, s));
+    MPC_TRY(msm_run<F>(bases, inf, scalars_dev, n, res, s, tbl));
     uint32_t* out = out_dev;
     if (!out) MPC_TRY(s_out.alloc(&out, 3 * N + 4, s));
     k_emit<F><<<1, 32, 0, s>>>(res, 1, mode, out);
@@ -697,8 +932,9 @@ int32_t msm_handle_host(uint64_t handle, size_t offset, const uint64_t* scalars,
     Fr* dsc;
     MPC_TRY(ss.alloc(&dsc, n, s));
     MPC_CUDA_TRY(cudaMemcpyAsync(dsc, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    TableRef tbl = table_of(v, offset);
     return msm_emit<F>((const Affine<F>*)v.bases + offset, v.inf ? v.inf + offset : nullptr, dsc, n, 0, nullptr, out_xy,
-                       out_inf, s);
+                       out_inf, s, &tbl);
 }
 
 template <class F>
@@ -766,15 +1002,24 @@ int32_t mpc_cuda_msm_release_bases(uint64_t handle) {
         v = it->second;
         g_bases.erase(it);
     }
+    int cur = 0;
+    MPC_CUDA_TRY(cudaGetDevice(&cur));
+    MPC_CUDA_TRY(cudaSetDevice(v.cuda_device));
     if (v.owned) {
-        int cur = 0;
-        MPC_CUDA_TRY(cudaGetDevice(&cur));
-        MPC_CUDA_TRY(cudaSetDevice(v.cuda_device));
         cudaFree(v.bases);
         if (v.inf) cudaFree(v.inf);
-        MPC_CUDA_TRY(cudaSetDevice(cur));
     }
+    if (v.table) cudaFree(v.table);
+    MPC_CUDA_TRY(cudaSetDevice(cur));
     return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_msm_g1_precompute(uint64_t handle, uint32_t window_bits) {
+    return precompute<Fq>(handle, window_bits, false);
+}
+
+int32_t mpc_cuda_msm_g2_precompute(uint64_t handle, uint32_t window_bits) {
+    return precompute<Fq2>(handle, window_bits, true);
 }
 
 int32_t mpc_cuda_msm_g1_handle(uint64_t handle, size_t offset, const uint64_t* scalars_mont, size_t n,
@@ -794,9 +1039,10 @@ int32_t mpc_cuda_msm_g1_handle_dev(uint64_t handle, size_t offset, const uint64_
     MPC_ARG_CHECK(out_jac_dev && (n == 0 || scalars_mont_dev));
     BaseVec v;
     MPC_TRY(find_bases(handle, false, offset, n, &v));
+    TableRef tbl = table_of(v, offset);
     return msm_emit<Fq>((const Affine<Fq>*)v.bases + offset, v.inf ? v.inf + offset : nullptr,
                         (const Fr*)scalars_mont_dev, n, 1, (uint32_t*)out_jac_dev, nullptr, nullptr,
-                        pick_stream(stream, s));
+                        pick_stream(stream, s), &tbl);
 }
 
 int32_t mpc_cuda_g1_sum_partials_dev(const uint64_t* jac_dev, uint32_t count, uint64_t out_xy[12], uint8_t* out_inf,

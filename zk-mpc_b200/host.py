@@ -189,6 +189,12 @@ class BaseHandle:
     def __init__(self, handle, n, g2):
         self.handle, self.n, self.g2 = handle, n, g2
 
+    def precompute(self, window_bits=0):
+        """build the 2^(c*w)*P table on the device (one shared bucket set per MSM afterwards)"""
+        _lib.call("mpc_cuda_msm_g2_precompute" if self.g2 else "mpc_cuda_msm_g1_precompute", C.c_uint64(self.handle),
+                  C.c_uint32(window_bits))
+        return self
+
     def release(self):
         if self.handle:
             _lib.call("mpc_cuda_msm_release_bases", C.c_uint64(self.handle))
