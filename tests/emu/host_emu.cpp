@@ -14,6 +14,9 @@ using Fr = Fp<consts::FrParams>;
 using Fq = Fp<consts::FqParams>;
 using Fq2 = Fp2<consts::FqParams>;
 
+template <class P> static Fp<P> sqr_wide_of(const Fp<P>& x) { return sqr_wide(x); }
+template <class P> static Fp2<P> sqr_wide_of(const Fp2<P>& x) { return sqr(x); }
+
 template <class F>
 static void vec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
     constexpr int N = F::N;
@@ -28,6 +31,7 @@ static void vec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, 
             case 3: r = neg(x); break;
             case 4: r = inv(x); break;
             case 7: r = sqr(x); break;
+            case 10: r = sqr_wide_of(x); break;
             case 9: r = dbl(x); break;
             default: r = x; break;
         }

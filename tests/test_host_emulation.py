@@ -65,6 +65,7 @@ def test_emulated_fr_fq(emu, orc, pkg):
             assert np.array_equal(_vec(emu, name, OPS[op], a, b), ofn(op, a, b)), (name, op)
         for op in ("neg", "sqr", "from_mont"):
             assert np.array_equal(_vec(emu, name, OPS[op], a), ofn(op, a)), (name, op)
+        assert np.array_equal(_vec(emu, name, 10, a), ofn("sqr", a)), (name, "dedicated squaring")
         assert np.array_equal(_vec(emu, name, OPS["to_mont"], ofn("from_mont", a)), a)
         assert np.array_equal(_vec(emu, name, OPS["inv"], a[:40]), ofn("inv", a[:40]))
 

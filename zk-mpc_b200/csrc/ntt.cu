@@ -98,7 +98,21 @@ DEV void sm_store(uint32_t* sm, uint32_t E, uint32_t e, const Fr& a) {
 }
 DEV uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? __brev(x) >> (32 - bits) : 0; }
 
-__global__ void __launch_bounds__(512) k_ntt_pass(PassArgs a) {
+// one DIF butterfly: u' = u + v, v' = (u - v) * w^k with w = ω_l, read from the forward table of domain l;
+// inverse transforms use ω^-k = -ω^(2^(l-1) - k) (the sign is folded into the subtraction order)
+DEV void bfly(Fr& u, Fr& v, const Fr* __restrict__ tw, size_t k, uint32_t l, bool inverse) {
+    bool swap = inverse && k != 0;
+    if (swap) k = ((size_t)1 << (l - 1)) - k;
+    Fr d = swap ? sub(v, u) : sub(u, v);
+    u = add(u, v);
+    v = l > 1 ? mul(d, load_fe_ro(tw + k)) : d;       // l == 1: the only twiddle is 1
+}
+
+// Every thread owns four rows of the tile and runs TWO stages on them in registers between
+// shared-memory exchanges (radix-4 step = 4 products, half the shared traffic and barriers of radix-2);
+// an odd stage count ends with one radix-2 stage.
+constexpr int NTT_THREADS = 256;
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
     extern __shared__ uint32_t sm[];
     const uint32_t t = threadIdx.x;
     const uint32_t rows = 1u << a.deg, C = 1u << a.lc, E = rows << a.lc;
@@ -107,6 +121,7 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassArgs a) {
     const size_t tile = blockIdx.x;
     const Fr* src = a.src + (size_t)blockIdx.y * n;
     Fr* dst = a.dst + (size_t)blockIdx.y * n;
+    const bool inverse = a.inverse != 0;
 
     // tile origin: non-last: i = origin + j*T + c;  last: i = (hb + (bitrev(c) << (s0-lc))) * rows + j
     size_t origin = 0, lo0 = 0, hb = 0;
@@ -119,10 +134,8 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassArgs a) {
         hb = bitrev((uint32_t)(tile << a.lc), a.s0);
     }
 
-    // ---- load two elements per thread
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        uint32_t e = t + h * (E / 2);
+    // ---- load
+    for (uint32_t e = t; e < E; e += blockDim.x) {
         uint32_t j, c;
         size_t i;
         if (!a.last) {
@@ -141,29 +154,46 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassArgs a) {
     }
     __syncthreads();
 
-    // ---- deg butterfly stages: lo' = lo + hi, hi' = (lo - hi) * w
-    const uint32_t c = t & (C - 1), q = t >> a.lc;
-    const size_t lo = a.last ? 0 : lo0 + c;
-    for (uint32_t r = 0; r < a.deg; r++) {
-        const uint32_t hbits = a.deg - 1 - r, half = 1u << hbits;
-        const uint32_t qq = q & (half - 1);
-        const uint32_t j0 = ((q >> hbits) << (hbits + 1)) | qq, j1 = j0 + half;
-        const uint32_t l = a.log_n - a.s0 - r;          // this stage is the first stage of a size-2^l DIF
-        size_t k = (size_t)qq * T + lo;
-        Fr u = sm_load(sm, E, (j0 << a.lc) + c), v = sm_load(sm, E, (j1 << a.lc) + c);
-        bool swap = a.inverse && k != 0;                 // ω^-k = -ω^(2^(l-1) - k)
-        if (swap) k = ((size_t)1 << (l - 1)) - k;
-        Fr d = swap ? sub(v, u) : sub(u, v);
-        if (l > 1) d = mul(d, load_fe_ro(a.tw[r] + k));  // l == 1: the only twiddle is 1
-        sm_store(sm, E, (j0 << a.lc) + c, add(u, v));
-        sm_store(sm, E, (j1 << a.lc) + c, d);
+    // ---- radix-4 rounds: stages r (half = 2h) and r+1 (half = h) on rows base + {0, h, 2h, 3h}
+    uint32_t r = 0;
+    for (; r + 2 <= a.deg; r += 2) {
+        const uint32_t hbits = a.deg - 2 - r, h = 1u << hbits;
+        const uint32_t l0 = a.log_n - a.s0 - r;
+        for (uint32_t item = t; item < E / 4; item += blockDim.x) {
+            const uint32_t c = item & (C - 1), q = item >> a.lc;
+            const size_t lo = a.last ? 0 : lo0 + c;
+            const uint32_t qq = q & (h - 1);
+            const uint32_t e0 = ((((q >> hbits) << (hbits + 2)) | qq) << a.lc) + c, es = h << a.lc;
+            Fr x0 = sm_load(sm, E, e0), x1 = sm_load(sm, E, e0 + es), x2 = sm_load(sm, E, e0 + 2 * es),
+               x3 = sm_load(sm, E, e0 + 3 * es);
+            bfly(x0, x2, a.tw[r], (size_t)qq * T + lo, l0, inverse);
+            bfly(x1, x3, a.tw[r], (size_t)(qq + h) * T + lo, l0, inverse);
+            bfly(x0, x1, a.tw[r + 1], (size_t)qq * T + lo, l0 - 1, inverse);
+            bfly(x2, x3, a.tw[r + 1], (size_t)qq * T + lo, l0 - 1, inverse);
+            sm_store(sm, E, e0, x0);
+            sm_store(sm, E, e0 + es, x1);
+            sm_store(sm, E, e0 + 2 * es, x2);
+            sm_store(sm, E, e0 + 3 * es, x3);
+        }
+        __syncthreads();
+    }
+    // ---- odd stage count: last stage of the pass (half = 1) pairs rows (2b, 2b+1)
+    if (r < a.deg) {
+        const uint32_t l0 = a.log_n - a.s0 - r;
+        for (uint32_t item = t; item < E / 2; item += blockDim.x) {
+            const uint32_t c = item & (C - 1), bq = item >> a.lc;
+            const size_t lo = a.last ? 0 : lo0 + c;
+            const uint32_t e0 = ((2 * bq) << a.lc) + c, es = C;
+            Fr x0 = sm_load(sm, E, e0), x1 = sm_load(sm, E, e0 + es);
+            bfly(x0, x1, a.tw[r], lo, l0, inverse);
+            sm_store(sm, E, e0, x0);
+            sm_store(sm, E, e0 + es, x1);
+        }
         __syncthreads();
     }
 
     // ---- store
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        uint32_t e = t + h * (E / 2);
+    for (uint32_t e = t; e < E; e += blockDim.x) {
         uint32_t j = e >> a.lc, cc = e & (C - 1);
         if (!a.last) {
             store_fe(dst + origin + (size_t)j * T + cc, sm_load(sm, E, e));
@@ -207,6 +237,9 @@ int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s,
     DomainCache& d = g_cache[dev_index];
     bool dirty = false;
     if (!d.ready) {
+        // 32 KB tiles: let several CTAs share an SM (the default carveout fits one)
+        MPC_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
         MPC_CUDA_TRY(cudaMalloc((void**)&d.consts, 144 * sizeof(Fr)));
         MPC_CUDA_TRY(cudaMalloc((void**)&d.gen_pair, 2 * sizeof(Fr)));
         k_domain_consts<<<1, 64, 0, s>>>(fr_from_limbs(consts::FR_TWO_ADIC_ROOT), fr_from_limbs(consts::FR_TWO_INV),
@@ -307,7 +340,8 @@ int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStr
         uint32_t E = (1u << deg) << a.lc;
         MPC_ARG_CHECK(tiles < ((size_t)1 << 31) && batch < 65536);
         dim3 grid((unsigned)tiles, batch);
-        k_ntt_pass<<<grid, E / 2, (size_t)E * sizeof(Fr), s>>>(a);
+        uint32_t threads = E / 4 < 32 ? 32 : (E / 4 > NTT_THREADS ? NTT_THREADS : E / 4);
+        k_ntt_pass<<<grid, threads, (size_t)E * sizeof(Fr), s>>>(a);
         MPC_KERNEL_CHECK();
         s0 += deg;
     }
