@@ -125,6 +125,15 @@ int32_t mpc_cuda_vec_op_dev(uint32_t op, const uint64_t* a, const uint64_t* b, c
 #define MPC_CUDA_NTT_COSET_IFFT 3
 int32_t mpc_cuda_ntt_fr(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch);
 int32_t mpc_cuda_ntt_fr_dev(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch, void* stream);
+/* Multi-GPU share NTT (one party's vector block-distributed over g = 2^log_g devices): the
+ * log_g stages that cross device boundaries.  After an all-to-all the caller holds data[q][l] for q < g and
+ * its slice l in [slice_offset, slice_offset + slice_len) of the n/g local offsets; this runs those stages
+ * (plus the coset / 1/g scaling of `kind`) in place.  Forward: all-to-all, cross stage, all-to-all back,
+ * local mpc_cuda_ntt_fr_dev(kind = FFT, log_n - log_g); device r, local m then holds X[m*g + bitrev(r)].
+ * Inverse: local IFFT, all-to-all, cross stage, all-to-all back -> natural block order.
+ * zk-mpc_b200/sharding.py drives it over torch.distributed (NCCL). */
+int32_t mpc_cuda_ntt_cross_stage_dev(uint64_t* data, uint32_t log_n, uint32_t log_g, size_t slice_offset,
+                                     size_t slice_len, uint32_t kind, void* stream);
 /* evals[i] *= (g^n - 1)^-1, g = 22  (EvaluationDomain::divide_by_vanishing_poly_on_coset_in_place) */
 int32_t mpc_cuda_divide_by_vanishing_on_coset(uint64_t* data, uint32_t log_n);
 int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n, void* stream);

@@ -348,6 +348,114 @@ int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStr
     return MPC_CUDA_OK;
 }
 
+
+// ---- multi-GPU: the stages that cross device boundaries -------------------------------------------------
+// With the vector block-distributed over g = 2^k devices (device q holds indices [q n/g, (q+1) n/g)), the
+// first k DIF stages pair elements n/2, n/4, ..., n/g apart, i.e. equal local offsets on different devices;
+// afterwards every block is an independent size-n/g transform (local k_ntt_pass).  After an all-to-all the
+// calling device holds, for its slice of local offsets l in [l0, l0 + len), the g values D[q][l]; one thread
+// runs the k cross stages for one offset in registers.  kind fft/coset_fft: (22^j scaling,) DIF stages
+// 0..k-1.  kind ifft/coset_ifft: the exact inverse (stages k-1..0 of t = hi w^-1, lo' = lo + t, hi' = lo - t,
+// then g^-1 and, for the coset, 22^-i).  Output layout of the forward transform: device r, local m holds
+// X[m g + bitrev_k(r)] (the usual transposed order of a four-step NTT); the inverse consumes that layout.
+constexpr int MAX_LOG_G = 3;
+
+struct CrossArgs {
+    Fr* data;                      // [g][len]
+    const Fr* tw[MAX_LOG_G];       // tw[s] = forward table of domain log_n - s
+    const Fr *g_lo, *g_hi;         // 22^(+-i) two-level tables (coset kinds), or nullptr
+    const Fr* scale;               // g^-1 (inverse kinds)
+    size_t l0, len;
+    uint32_t log_n, log_g, inverse;
+};
+
+template <int LOG_G>
+__global__ void __launch_bounds__(128) k_ntt_cross(CrossArgs a) {
+    constexpr int G = 1 << LOG_G;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.len) return;
+    const size_t n = (size_t)1 << a.log_n, blk = n >> LOG_G, l = a.l0 + t;
+    const bool inverse = a.inverse != 0;
+    Fr x[G];
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        x[q] = load_fe(a.data + (size_t)q * a.len + t);
+        if (!inverse && a.g_lo) {
+            size_t j = (size_t)q * blk + l;
+            x[q] = mul(x[q], load_fe_ro(a.g_lo + (j & ((1u << COSET_LO_BITS) - 1))));
+            if (a.log_n > COSET_LO_BITS) x[q] = mul(x[q], load_fe_ro(a.g_hi + (j >> COSET_LO_BITS)));
+        }
+    }
+    if (!inverse) {
+#pragma unroll
+        for (int s = 0; s < LOG_G; s++) {
+            const int dist = G >> (s + 1);
+            const size_t half = n >> (s + 1);
+#pragma unroll
+            for (int q = 0; q < G; q++) {
+                if (q & dist) continue;
+                size_t k = ((size_t)q * blk + l) & (half - 1);
+                bfly(x[q], x[q + dist], a.tw[s], k, a.log_n - s, false);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int s = LOG_G - 1; s >= 0; s--) {
+            const int dist = G >> (s + 1);
+            const size_t half = n >> (s + 1);
+            const uint32_t lg = a.log_n - s;
+#pragma unroll
+            for (int q = 0; q < G; q++) {
+                if (q & dist) continue;
+                size_t k = ((size_t)q * blk + l) & (half - 1);
+                // t = hi * w^-k with w^-k = -w^(2^(lg-1) - k) for k != 0
+                Fr tv = x[q + dist];
+                if (lg > 1) tv = mul(tv, load_fe_ro(a.tw[s] + (k ? ((size_t)1 << (lg - 1)) - k : 0)));
+                if (k) { x[q + dist] = add(x[q], tv); x[q] = sub(x[q], tv); }
+                else { x[q + dist] = sub(x[q], tv); x[q] = add(x[q], tv); }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        if (inverse) {
+            x[q] = mul(x[q], load_fe_ro(a.scale));
+            if (a.g_lo) {
+                size_t i = (size_t)q * blk + l;
+                x[q] = mul(x[q], load_fe_ro(a.g_lo + (i & ((1u << COSET_LO_BITS) - 1))));
+                if (a.log_n > COSET_LO_BITS) x[q] = mul(x[q], load_fe_ro(a.g_hi + (i >> COSET_LO_BITS)));
+            }
+        }
+        store_fe(a.data + (size_t)q * a.len + t, x[q]);
+    }
+}
+
+int32_t ntt_cross_dev(Fr* data, uint32_t log_n, uint32_t log_g, size_t l0, size_t len, uint32_t kind, cudaStream_t s) {
+    MPC_ARG_CHECK(kind <= MPC_CUDA_NTT_COSET_IFFT && log_g >= 1 && log_g <= (uint32_t)MAX_LOG_G);
+    MPC_ARG_CHECK(log_n <= MAX_LOG_N && log_n > log_g && l0 + len <= ((size_t)1 << (log_n - log_g)));
+    if (len == 0) return MPC_CUDA_OK;
+    MPC_ARG_CHECK(data != nullptr);
+    const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
+    const bool coset = kind >= MPC_CUDA_NTT_COSET_FFT;
+    DomainCache* d;
+    MPC_TRY(ensure_tables(current_device_index(), log_n, coset, s, &d));
+    CrossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.data = data;
+    for (uint32_t st = 0; st < log_g; st++) a.tw[st] = d->tw[log_n - st];
+    if (coset) { a.g_lo = inverse ? d->gi_lo : d->g_lo; a.g_hi = inverse ? d->gi_hi : d->g_hi; }
+    a.scale = d->consts + 48 + log_g;
+    a.l0 = l0; a.len = len; a.log_n = log_n; a.log_g = log_g; a.inverse = inverse;
+    unsigned blocks = (unsigned)((len + 127) / 128);
+    switch (log_g) {
+        case 1: k_ntt_cross<1><<<blocks, 128, 0, s>>>(a); break;
+        case 2: k_ntt_cross<2><<<blocks, 128, 0, s>>>(a); break;
+        default: k_ntt_cross<3><<<blocks, 128, 0, s>>>(a); break;
+    }
+    MPC_KERNEL_CHECK();
+    return MPC_CUDA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -356,6 +464,13 @@ int32_t mpc_cuda_ntt_fr_dev(uint64_t* data, uint32_t log_n, uint32_t kind, uint3
     cudaStream_t s;
     MPC_TRY(enter(&s));
     return ntt_dev((Fr*)data, log_n, kind, batch, pick_stream(stream, s));
+}
+
+int32_t mpc_cuda_ntt_cross_stage_dev(uint64_t* data, uint32_t log_n, uint32_t log_g, size_t slice_offset,
+                                     size_t slice_len, uint32_t kind, void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    return ntt_cross_dev((Fr*)data, log_n, log_g, slice_offset, slice_len, kind, pick_stream(stream, s));
 }
 
 int32_t mpc_cuda_ntt_fr(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch) {

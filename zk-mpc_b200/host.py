@@ -297,3 +297,15 @@ def profile_read(name):
     ms, cnt = C.c_double(0), C.c_uint64(0)
     _lib.call("mpc_cuda_profile_read", name.encode(), C.byref(ms), C.byref(cnt))
     return ms.value, cnt.value
+
+
+def ntt_dev(ptr, log_n, kind, batch=1, stream=None):
+    """in-place NTT of device-resident data (ptr: integer device address)"""
+    _lib.call("mpc_cuda_ntt_fr_dev", C.cast(ptr, u64p), C.c_uint32(log_n), C.c_uint32(NTT_KIND[kind]), C.c_uint32(batch),
+              C.c_void_p(stream) if stream else None)
+
+
+def ntt_cross_stage_dev(ptr, log_n, log_g, slice_offset, slice_len, kind, stream=None):
+    _lib.call("mpc_cuda_ntt_cross_stage_dev", C.cast(ptr, u64p), C.c_uint32(log_n), C.c_uint32(log_g),
+              C.c_size_t(slice_offset), C.c_size_t(slice_len), C.c_uint32(NTT_KIND[kind]),
+              C.c_void_p(stream) if stream else None)

@@ -43,3 +43,57 @@ def sharded_msm(dist, rank, world, n, local_partial, sum_partials, device=None):
     if rank != 0:
         return None
     return sum_partials(gathered.cpu().numpy().view(np.uint64).reshape(world, -1))
+
+
+# ----------------------------------------------------------------------------- multi-GPU share NTT
+def bitrev(x, bits):
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (x & 1)
+        x >>= 1
+    return r
+
+
+def ntt_output_owner(i, world):
+    """(rank, local index) of forward output X[i] when the transform ran over `world` = 2^k devices"""
+    k = world.bit_length() - 1
+    return bitrev(i % world, k), i // world
+
+
+def _all_to_all(dist, send, world):
+    """send: (world, slice, 4) tensor, chunk q goes to rank q; returns (world, slice, 4) with chunk q from rank q"""
+    import torch
+    recv = torch.empty_like(send)
+    if dist.get_backend() == "gloo":          # CPU tests: gloo has no all_to_all_single on every build
+        everything = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(everything, send.contiguous())
+        rank = dist.get_rank()
+        for q in range(world):
+            recv[q] = everything[q][rank]
+        return recv
+    dist.all_to_all_single(recv, send.contiguous())
+    return recv
+
+
+def dist_ntt(dist, rank, world, block, log_n, kind, cross_stage, local_ntt):
+    """One party's size-2^log_n NTT over `world` = 2^k ranks (include/mpc_cuda.h
+    mpc_cuda_ntt_cross_stage_dev).  `block`: (n/world, 4) int64 tensor, this rank's part of the vector —
+    natural block order for the forward kinds (fft, coset_fft), the transposed order the forward kinds
+    produce (ntt_output_owner) for the inverse kinds, which return natural block order.
+    cross_stage(data (world, slice, 4) tensor, l0, kind) and local_ntt(block tensor, kind) run in place
+    (C ABI on the GPU; models in the CPU test).  Two all-to-alls of (world-1)/world of the block each."""
+    inverse = kind in ("ifft", "coset_ifft")
+    if world == 1:
+        local_ntt(block, kind)
+        return block
+    m = block.shape[0]
+    slice_len = m // world
+    assert slice_len * world == m and m * world == 1 << log_n
+    if inverse:
+        local_ntt(block, "ifft")
+    data = _all_to_all(dist, block.view(world, slice_len, 4), world)
+    cross_stage(data, rank * slice_len, kind)
+    block = _all_to_all(dist, data, world).view(m, 4)
+    if not inverse:
+        local_ntt(block, "fft")
+    return block
