@@ -165,6 +165,8 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     pkg = ge.load_package()
@@ -338,12 +340,16 @@ def run_gpu(args):
         t, cnt = H.profile_read("ntt")
         ms = max_over_ranks(t / max(cnt, 1))
         gbs = NTT_BYTES_PER_ELEM * n / (ms * 1e-3) / 1e9
+        gimad = (n / 2) * log_n * 136.0 / (ms * 1e-3) / 1e9           # 136 IMAD per butterfly
         extra["ntt_" + name] = {"value": world * n / (ms * 1e-3) / 1e6, "unit": "Melem/s", "ms": ms, "log_n": log_n,
                                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                              "frac": gbs / hbm_peak, "traffic": traffic.get("k_ntt_pass", n),
                                              "passes": (log_n + 7) // 8,
-                                             "note": "64 B/element algorithmic; butterflies cost ~136 IMAD each, "
-                                                     "so the integer pipe, not HBM, is the ceiling (SURVEY.md 8d)"}}
+                                             "int_pipe": {"achieved": gimad, "peak": imad_peak, "unit": "GIMAD/s",
+                                                          "frac": gimad / imad_peak},
+                                             "note": "64 B/element algorithmic (traffic is per pass); butterflies cost "
+                                                     "~136 IMAD each, so the integer pipe, not HBM, is the ceiling "
+                                                     "(SURVEY.md 8d): int_pipe is the binding fraction"}}
     H.set_option("profile", 0)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for it in range(args.warmup + args.steps):

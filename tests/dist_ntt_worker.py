@@ -25,7 +25,7 @@ def main():
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
     log_g = world.bit_length() - 1
-    for log_n in [int(x) for x in sys.argv[1:]] or [log_g + 1, 8, 13, 16]:
+    for log_n in [int(x) for x in sys.argv[1:]] or [2 * log_g, 8, 13, 16]:
         n = 1 << log_n
         m = n // world
         full = S.fr_uniform(0x900 + log_n, n)
