@@ -138,6 +138,20 @@ int32_t mpc_cuda_ntt_cross_stage_dev(uint64_t* data, uint32_t log_n, uint32_t lo
 int32_t mpc_cuda_divide_by_vanishing_on_coset(uint64_t* data, uint32_t log_n);
 int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n, void* stream);
 
+/* ---- fused witness map ---------------------------------------------------------------------
+ * R1CStoQAP::witness_map on one party's local values (src/groth16.rs:278-303), additive shares.  The
+ * vectors stay in HBM between the calls; only the masked values cross PCIe for the two opens, which stay
+ * on mpc-net.  begin: a, b, c = the party's evaluations of the A, B, C polynomials over the domain
+ * (2^log_n elements each), tx, ty = its Beaver triple shares; computes a' = coset_fft(ifft(a)) (same for
+ * b, c) and returns masked_a = a' + tx, masked_b = b' + ty.  finish: tz = triple share, sx / oy = the
+ * opened sums of masked_a / masked_b over the parties; returns this party's share of
+ * h = coset_ifft((a'*b' - c') / Z_H).  finish always releases the state. */
+int32_t mpc_cuda_witness_map_begin(const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,
+                                   const uint64_t* tx, const uint64_t* ty, uint64_t* masked_a, uint64_t* masked_b,
+                                   uint64_t* state);
+int32_t mpc_cuda_witness_map_finish(uint64_t state, const uint64_t* tz, const uint64_t* sx, const uint64_t* oy,
+                                    uint32_t is_leader, uint64_t* h_out);
+
 /* ---- share MSM ------------------------------------------------------------------------------
  * Msm::msm / AffineMsm::msm (mpc-algebra/src/share/msm.rs:6-9,33-37) =
  * AffineCurve::multi_scalar_mul (arkworks/algebra/ec/src/lib.rs:305-314: into_repr each scalar) +

@@ -99,3 +99,26 @@ def test_witness_map_sequence(H, orc, pkg):
     got = seq(H, H.ntt, H.vec_op, H.divide_by_vanishing_on_coset)
     exp = seq(orc, orc.ntt, orc.vec_op, orc.divide_by_vanishing_on_coset)
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("log_n", [3, 13])
+def test_fused_witness_map_three_parties(H, orc, pkg, log_n):
+    """mpc_cuda_witness_map_begin/finish for 3 parties with the reference's dummy triples (leader 1, others 0;
+    mpc-algebra/src/wire/field.rs:44-63), the two opens played by open_sum: the opened h equals the plain
+    witness_map of the opened inputs computed by the oracle."""
+    S = pkg.synth
+    n, parties = 1 << log_n, 3
+    sh = [[S.fr_uniform(0x700 + 10 * p + k, n) for k in range(3)] for p in range(parties)]      # a, b, c shares
+    one, zero = np.tile(S.FR_R_LIMBS, (n, 1)), np.zeros((n, 4), dtype=np.uint64)
+    trip = [(one, one, one)] + [(zero, zero, zero)] * (parties - 1)
+    begun = [H.witness_map_begin(sh[p][0], sh[p][1], sh[p][2], trip[p][0], trip[p][1]) for p in range(parties)]
+    sx = H.open_sum(np.stack([bg[0] for bg in begun]))
+    oy = H.open_sum(np.stack([bg[1] for bg in begun]))
+    hs = [H.witness_map_finish(begun[p][2], trip[p][2], sx, oy, p == 0) for p in range(parties)]
+    got = H.open_sum(np.stack(hs))
+    a, b, c = (orc.open_sum(np.stack([sh[p][k] for p in range(parties)])) for k in range(3))
+    a1, b1, c1 = (orc.ntt(orc.ntt(v, "ifft"), "coset_fft") for v in (a, b, c))
+    exp = orc.ntt(orc.divide_by_vanishing_on_coset(orc.vec_op("sub", orc.vec_op("mul", a1, b1), c1)), "coset_ifft")
+    assert np.array_equal(got, exp)
+    with pytest.raises(H.MpcCudaError):
+        H.witness_map_finish(begun[0][2], trip[0][2], sx, oy, True)        # state already consumed

@@ -309,3 +309,28 @@ def ntt_cross_stage_dev(ptr, log_n, log_g, slice_offset, slice_len, kind, stream
     _lib.call("mpc_cuda_ntt_cross_stage_dev", C.cast(ptr, u64p), C.c_uint32(log_n), C.c_uint32(log_g),
               C.c_size_t(slice_offset), C.c_size_t(slice_len), C.c_uint32(NTT_KIND[kind]),
               C.c_void_p(stream) if stream else None)
+
+
+# ----------------------------------------------------------------------------- fused witness map
+def witness_map_begin(a, b, c, tx, ty):
+    """first half of R1CStoQAP::witness_map (src/groth16.rs:278-285) on the device; returns
+    (masked_a, masked_b, state) — the masked vectors are what the party broadcasts for the two opens"""
+    a, b, c, tx, ty = (_a(v, 4) for v in (a, b, c, tx, ty))
+    n = a.size // 4
+    log_n = n.bit_length() - 1
+    if (1 << log_n) != n or any(v.shape != a.shape for v in (b, c, tx, ty)):
+        raise ValueError("witness_map needs five equal power-of-two vectors")
+    ma, mb = np.empty_like(a), np.empty_like(a)
+    st = C.c_uint64(0)
+    _lib.call("mpc_cuda_witness_map_begin", _p(a), _p(b), _p(c), C.c_uint32(log_n), _p(tx), _p(ty), _p(ma), _p(mb),
+              C.byref(st))
+    return ma, mb, st.value
+
+
+def witness_map_finish(state, tz, sx, oy, is_leader):
+    """second half (src/groth16.rs:285-303): Beaver combine, - c, / Z_H on the coset, coset iFFT"""
+    tz, sx, oy = _a(tz, 4), _a(sx, 4), _a(oy, 4)
+    h = np.empty_like(tz)
+    _lib.call("mpc_cuda_witness_map_finish", C.c_uint64(state), _p(tz), _p(sx), _p(oy),
+              C.c_uint32(int(bool(is_leader))), _p(h))
+    return h
