@@ -143,7 +143,11 @@ Plan make_plan(size_t n, int sm_count, uint32_t table_c) {
     size_t nbuckets = (size_t)p.snwin * p.nb;
     p.max_tasks = n * (size_t)p.nwin / p.task_len + nbuckets + 1;
     p.scan_blocks = (uint32_t)((nbuckets + SCAN_ITEMS - 1) / SCAN_ITEMS);
-    p.red_m = p.nb < 32 ? p.nb : (p.nb > (1u << 16) ? 64 : 32);
+    // bucket-reduce chunk: short chunks (more threads, shorter serial chains) while the grid stays small,
+    // longer ones once there are enough chunks to fill the machine
+    p.red_m = p.nb > (1u << 16) ? 64 : 32;
+    while (p.red_m > 4 && (size_t)p.snwin * (p.nb / p.red_m) < (size_t)sm_count * 128) p.red_m >>= 1;
+    if (p.red_m > p.nb) p.red_m = p.nb;
     p.red_t = p.nb / p.red_m;
     p.sum_parts = (p.red_t + 1023) / 1024;       // <= 1024 chunk results per first-level block
     return p;
