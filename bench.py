@@ -365,6 +365,26 @@ def run_gpu(args):
     extra["beaver_combine"] = {"value": world * n / (ms * 1e-3) / 1e6, "unit": "Melem/s", "ms": ms,
                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                             "frac": gbs / hbm_peak, "traffic": traffic.get("k_combine", n)}}
+    if world > 1 and (world & (world - 1)) == 0 and world <= 8:
+        # one party's 2^log_n NTT block-distributed over the ranks (strong scaling; two NCCL all-to-alls
+        # around the cross-device stages, sharding.dist_ntt)
+        log_g = world.bit_length() - 1
+        m = n // world
+        blockv = vec[: m].clone()
+        cross = lambda data, l0, kind: H.ntt_cross_stage_dev(data.data_ptr(), log_n, log_g, l0, data.shape[1], kind, sptr.value)
+        local_ntt = lambda blk, kind: H.ntt_dev(blk.data_ptr(), log_n - log_g, kind, 1, sptr.value)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(args.warmup + args.steps):
+            if it == args.warmup:
+                barrier()
+                d0.record(stream)
+            pkg.sharding.dist_ntt(dist, rank, world, blockv, log_n, "fft", cross, local_ntt)
+        d1.record(stream)
+        barrier()
+        ms = max_over_ranks(d0.elapsed_time(d1) / args.steps)
+        extra["ntt_fft_sharded"] = {"value": n / (ms * 1e-3) / 1e6, "unit": "Melem/s", "ms": ms, "log_n": log_n,
+                                    "scaling": "strong", "exchange": "2 x all_to_all_single of (g-1)/g of each block (NCCL)",
+                                    "nvlink_bytes_per_gpu": 2 * (world - 1) * (m // world) * 32}
     extra["hbm_peak_source"] = hbm_src
     extra["msm_without_table"] = {"value": world * n / (plain_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": plain_ms,
                                   "stage_ms": plain_stage, "note": "resident CRS, no precomputed window table"}
