@@ -165,9 +165,18 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        # NCCL prints its version banner on stdout when the first communicator is created: send fd 1 to
+        # stderr until that has happened, so stdout carries exactly the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     pkg = ge.load_package()
     if not os.path.exists(pkg._lib.LIB_PATH):
