@@ -374,6 +374,42 @@ def run_gpu(args):
     extra["beaver_combine"] = {"value": world * n / (ms * 1e-3) / 1e6, "unit": "Melem/s", "ms": ms,
                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                             "frac": gbs / hbm_peak, "traffic": traffic.get("k_combine", n)}}
+    # SPDZ layout of the same kernel: [sh | mac] planes, 320 B per share pair
+    sp_in = [torch.cat([t, t]) for t in others[:3]]
+    sp_out = torch.empty_like(sp_in[0])
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            barrier()
+            evs[0].record(stream)
+        L.call("mpc_cuda_beaver_combine_dev", *[C.cast(t.data_ptr(), L.u64p) for t in sp_in],
+               C.cast(others[3].data_ptr(), L.u64p), C.cast(others[4].data_ptr(), L.u64p),
+               C.cast(sp_out.data_ptr(), L.u64p), C.c_size_t(n), C.c_uint32(1), C.c_uint32(1), sptr)
+    evs[1].record(stream)
+    barrier()
+    ms = max_over_ranks(evs[0].elapsed_time(evs[1]) / args.steps)
+    gbs = 320.0 * n / (ms * 1e-3) / 1e9
+    extra["beaver_combine_spdz"] = {"value": world * n / (ms * 1e-3) / 1e6, "unit": "Melem/s", "ms": ms,
+                                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                                 "frac": gbs / hbm_peak, "traffic": None}}
+    del sp_in, sp_out
+
+    # share MSM over G2 (b_g2_query, src/groth16.rs:160): 2^20 points per GPU, resident CRS, no table
+    g2_log = min(20, log_n)
+    g2_n = 1 << g2_log
+    g2_dev = H.g2_generate(seed, g2_n, first=rank * g2_n)
+    g2_host = g2_dev.download().reshape(g2_n, 24)
+    g2_dev.free()
+    g2_handle = H.register_bases(g2_host, g2=True)
+    g2_sc = scalars_host.numpy().view(np.uint64).reshape(n, 4)[:g2_n]
+    H.msm_handle(g2_handle, g2_sc)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        H.msm_handle(g2_handle, g2_sc)
+    g2_s = max_over_ranks((time.perf_counter() - t0) / 3)
+    g2_handle.release()
+    extra["msm_g2"] = {"value": world * g2_n / g2_s / 1e6, "unit": "Mpts/s", "ms": g2_s * 1e3, "log_n": g2_log,
+                       "api": "mpc_cuda_msm_g2_handle (host scalars, resident CRS)"}
+
     if world > 1 and (world & (world - 1)) == 0 and world <= 8:
         # one party's 2^log_n NTT block-distributed over the ranks (strong scaling; two NCCL all-to-alls
         # around the cross-device stages, sharding.dist_ntt)
