@@ -31,7 +31,7 @@ template <class P> HD Fp<P> mul5(const Fp<P>& a) { return add(dbl(dbl(a)), a); }
 
 // Karatsuba: (a0 + a1 u)(b0 + b1 u) = (a0 b0 - 5 a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u
 template <class P>
-HD Fp2<P> mul(const Fp2<P>& a, const Fp2<P>& b) {
+HD_NOINLINE Fp2<P> mul(const Fp2<P>& a, const Fp2<P>& b) {
     Fp<P> v0 = mul(a.c0, b.c0);
     Fp<P> v1 = mul(a.c1, b.c1);
     Fp<P> s = mul(add(a.c0, a.c1), add(b.c0, b.c1));
@@ -43,7 +43,7 @@ HD Fp2<P> mul(const Fp2<P>& a, const Fp2<P>& b) {
 
 // complex squaring: c1 = 2 a0 a1, c0 = (a0 + a1)(a0 - 5 a1) + 4 a0 a1
 template <class P>
-HD Fp2<P> sqr(const Fp2<P>& a) {
+HD_NOINLINE Fp2<P> sqr(const Fp2<P>& a) {
     Fp<P> v = mul(a.c0, a.c1);
     Fp<P> t = mul(add(a.c0, a.c1), sub(a.c0, mul5(a.c1)));
     Fp2<P> r;

@@ -15,9 +15,13 @@
 #if defined(__CUDACC__)
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
+// out-of-line on the device: used for the Fq2 products, whose full inlining into the G2 group law made
+// single kernels of >100k instructions and a 25-minute ptxas run
+#define HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define HD inline
 #define DEV inline
+#define HD_NOINLINE inline
 #endif
 
 namespace ptx {
