@@ -37,7 +37,9 @@ extern "C" {
 #define MPC_CUDA_ERR_HANDLE 4     /* unknown handle */
 
 /* ---- context ------------------------------------------------------------------------------- */
-/* Select the devices the library may use (NULL/0 = all visible).  Idempotent, thread-safe. */
+/* Select the devices the library may use (NULL/0 = all visible).  Thread-safe.  Idempotent for the same
+ * list (or NULL/0); once initialised — explicitly or lazily by any other call — a DIFFERENT explicit list
+ * returns MPC_CUDA_ERR_ARG: the per-device caches are keyed by list position. */
 int32_t mpc_cuda_init(const int32_t* devices, int32_t n_dev);
 /* Party identity of the calling thread: leader = party 0 (mpc-net/src/lib.rs:49-51); the thread's
  * default device becomes devices[party_id % n_dev]. */
@@ -45,9 +47,10 @@ int32_t mpc_cuda_set_party(uint32_t party_id, uint32_t n_parties);
 /* Explicit device for the calling thread (index into the init list). */
 int32_t mpc_cuda_set_device(int32_t dev_index);
 int32_t mpc_cuda_device_count(void);
-/* Tuning knobs for benchmarks and tests (process-wide; 0 restores the automatic choice):
+/* Tuning knobs for benchmarks and tests (process-wide atomics; 0 restores the automatic choice):
  *   "msm_window_bits"  Pippenger window width c (3..23)
  *   "msm_task_len"     maximum points one accumulation task adds (bucket splitting)
+ *   "msm_host_chunks"  point-range chunks a host-buffer MSM is streamed in (copy/compute overlap), 1..16
  *   "profile"          1: bracket pipeline stages with CUDA events on the launching stream */
 int32_t mpc_cuda_set_option(const char* name, int64_t value);
 /* Number of kernels this library has launched so far (all threads). */
@@ -134,6 +137,22 @@ int32_t mpc_cuda_ntt_fr_dev(uint64_t* data, uint32_t log_n, uint32_t kind, uint3
  * zk-mpc_b200/sharding.py drives it over torch.distributed (NCCL). */
 int32_t mpc_cuda_ntt_cross_stage_dev(uint64_t* data, uint32_t log_n, uint32_t log_g, size_t slice_offset,
                                      size_t slice_len, uint32_t kind, void* stream);
+/* The same transform inside ONE process over g = 2^log_g devices of the init list: blocks[q] is a device
+ * pointer on device dev_index[q] (NULL = q) to block q (n/g elements).  The cross-device stages read and write
+ * the peers' blocks directly over NVLink inside the butterfly kernel (no separate all-to-all), then every
+ * device runs its local transform.  Layouts as above: forward kinds take natural block order and leave device r,
+ * local m = X[m*g + bitrev(r)]; inverse kinds take that order and return natural block order.  Asynchronous:
+ * the work is ordered on the calling thread's streams of the devices; when it returns, the stream of
+ * dev_index[0] is ordered after the whole transform (mpc_cuda_set_device + mpc_cuda_stream_sync(NULL) waits).
+ * All dev_index equal = g virtual devices on one GPU (used by the single-GPU parity tests). */
+int32_t mpc_cuda_ntt_fr_sharded_dev(uint64_t* const* blocks, const int32_t* dev_index, uint32_t log_n, uint32_t log_g,
+                                    uint32_t kind);
+/* natural block order <-> transposed order across the devices (out of place; to_transposed = 1: natural in) */
+int32_t mpc_cuda_ntt_reorder_sharded_dev(uint64_t* const* in, uint64_t* const* out, const int32_t* dev_index,
+                                         uint32_t log_n, uint32_t log_g, uint32_t to_transposed);
+/* Host vector, in-order in and out exactly like mpc_cuda_ntt_fr (batch 1), computed on 2^log_g devices: block q
+ * crosses its own PCIe link, synchronous. */
+int32_t mpc_cuda_ntt_fr_sharded(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t log_g);
 /* evals[i] *= (g^n - 1)^-1, g = 22  (EvaluationDomain::divide_by_vanishing_poly_on_coset_in_place) */
 int32_t mpc_cuda_divide_by_vanishing_on_coset(uint64_t* data, uint32_t log_n);
 int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n, void* stream);
@@ -168,6 +187,16 @@ int32_t mpc_cuda_msm_g2(const uint64_t* bases_xy, const uint8_t* inf, const uint
 int32_t mpc_cuda_msm_g1_register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle);
 int32_t mpc_cuda_msm_g1_register_bases_dev(const uint64_t* bases_xy_dev, size_t n, uint64_t* handle);
 int32_t mpc_cuda_msm_g2_register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle);
+int32_t mpc_cuda_msm_g2_register_bases_dev(const uint64_t* bases_xy_dev, size_t n, uint64_t* handle);
+/* Multi-GPU inside ONE process: the vector is cut into `parts` point ranges, range k resident on
+ * device (k mod n_dev) of the init list.  mpc_cuda_msm_g{1,2}_handle / _precompute on such a handle run every part on its
+ * own device concurrently (the caller still sees one msm call, mpc-algebra/src/share/msm.rs:6-9); the Jacobian
+ * partials are gathered over NVLink peer copies and added on the calling thread's device. */
+int32_t mpc_cuda_msm_g1_register_bases_sharded(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint32_t parts,
+                                               uint64_t* handle);
+int32_t mpc_cuda_msm_g2_register_bases_sharded(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint32_t parts,
+                                               uint64_t* handle);
+/* Drops the registry's reference; the memory is freed once no concurrent call still uses the vector. */
 int32_t mpc_cuda_msm_release_bases(uint64_t handle);
 /* Optional, once per registered CRS: build the table 2^(c*w) * P_i for every window w (c = window_bits,
  * 0 = automatic; nwin x the size of the vector in HBM).  Later MSMs over the handle use one shared bucket
@@ -185,9 +214,17 @@ int32_t mpc_cuda_msm_g2_handle(uint64_t handle, size_t offset, const uint64_t* s
  * (multi-GPU point-range sharding) */
 int32_t mpc_cuda_msm_g1_handle_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
                                    uint64_t* out_jac_dev /*18*/, void* stream);
+int32_t mpc_cuda_msm_g2_handle_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
+                                   uint64_t* out_jac_dev /*36*/, void* stream);
 /* affine(sum of `count` Jacobian partials); partials on the device, result on the host */
 int32_t mpc_cuda_g1_sum_partials_dev(const uint64_t* jac_dev /*count*18*/, uint32_t count,
                                      uint64_t out_xy[12], uint8_t* out_inf, void* stream);
+int32_t mpc_cuda_g2_sum_partials_dev(const uint64_t* jac_dev /*count*36*/, uint32_t count,
+                                     uint64_t out_xy[24], uint8_t* out_inf, void* stream);
+/* whole-vector MSM over a sharded handle with the scalars already resident: scalars_mont_dev[k] is a pointer on
+ * device k to the scalars of part k's point range (n/parts (+1) elements, same split as registration) */
+int32_t mpc_cuda_msm_g1_handle_sharded_dev(uint64_t handle, const uint64_t* const* scalars_mont_dev, uint32_t parts,
+                                           uint64_t out_xy[12], uint8_t* out_inf);
 
 /* Synthetic CRS for benchmarks and tests: bases[i] = k_i * G1 generator with
  * k_i = max(1, mix64(seed + (first+i+1)*0x9E3779B97F4A7C15)), written as affine x|y to device memory. */
@@ -197,7 +234,8 @@ int32_t mpc_cuda_g2_generate_dev(uint64_t seed, size_t first, size_t n, uint64_t
 /* ---- diagnostics ----------------------------------------------------------------------------
  * Raw field kernels (one element per thread) used by the parity tests to pin the device
  * arithmetic itself: field 0 = Fr (4 limbs), 1 = Fq (6 limbs); op 0 add, 1 sub, 2 mul, 3 neg,
- * 4 inverse (0 -> 0), 5 Montgomery->canonical, 6 canonical->Montgomery, 7 square. */
+ * 4 inverse (0 -> 0), 5 Montgomery->canonical, 6 canonical->Montgomery, 7 square, 8 product through the
+ * 32-bit-column formulation, 9 inverse through the binary-Euclid routine of the result-emission tail. */
 int32_t mpc_cuda_field_op(uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* Integer-pipe microbenchmark: returns achieved giga-ops/s of `iters` dependent instructions per
  * thread over a full-chip grid.  kind 0 = IMAD.U32 (32-bit), 1 = IMAD.WIDE.U32 with carry chain,

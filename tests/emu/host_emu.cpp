@@ -33,6 +33,7 @@ static void vec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, 
             case 7: r = sqr(x); break;
             case 10: r = sqr_wide_of(x); break;
             case 9: r = dbl(x); break;
+            case 11: r = inv_euclid(x); break;
             default: r = x; break;
         }
         memcpy(out + N * i, &r, 4 * N);
@@ -93,7 +94,24 @@ static void ec_mul_small(const uint32_t* pt, uint64_t k, uint32_t* out_xy, uint8
     memcpy(out_xy + N, &oy, 4 * N);
 }
 
+// 2^k * P through the Jacobian doubling of the window-table builder, normalised with the Euclid inversion
+template <class F>
+static void ec_jac_dbl_chain(const uint32_t* pt, uint32_t k, uint32_t* out_xy) {
+    constexpr int N = F::N;
+    Jac<F> j;
+    memcpy(&j.x, pt, 4 * N);
+    memcpy(&j.y, pt + N, 4 * N);
+    j.z = F::one();
+    for (uint32_t i = 0; i < k; i++) jac_dbl(j);
+    F zi = inv_euclid(j.z), zi2 = sqr(zi);
+    F ox = mul(j.x, zi2), oy = mul(j.y, mul(zi2, zi));
+    memcpy(out_xy, &ox, 4 * N);
+    memcpy(out_xy + N, &oy, 4 * N);
+}
+
 extern "C" {
+void emu_g1_jac_dbl_chain(const uint32_t* pt, uint32_t k, uint32_t* out_xy) { ec_jac_dbl_chain<Fq>(pt, k, out_xy); }
+void emu_g2_jac_dbl_chain(const uint32_t* pt, uint32_t k, uint32_t* out_xy) { ec_jac_dbl_chain<Fq2>(pt, k, out_xy); }
 void emu_fr_vec(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
     if (op == 5 || op == 6) vec_op_mont<Fr>(op, a, out, n); else vec_op<Fr>(op, a, b, out, n);
 }

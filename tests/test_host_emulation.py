@@ -173,3 +173,29 @@ def test_signed_digit_recoding(emu, pkg, c):
             assert not (d >> 31 and mag == 0)
             total += (-mag if d >> 31 else mag) << (c * w)
         assert total == v
+
+
+def test_emulated_euclid_inverse(emu, orc, pkg):
+    """inv_euclid (the binary extended Euclid of ff/src/fields/macros.rs:389-443) == the Fermat ladder == oracle"""
+    a = _edge_fr(pkg, 300, 21)
+    assert np.array_equal(_vec(emu, "emu_fr_vec", 11, a), orc.fr("inv", a))
+    q = _edge_fq(300, 22)
+    assert np.array_equal(_vec(emu, "emu_fq_vec", 11, q), orc.fq("inv", q))
+    q2 = np.concatenate([_edge_fq(60, 23), _edge_fq(60, 24)[::-1]], axis=1)
+    assert np.array_equal(_vec(emu, "emu_fq2_vec", 11, q2), orc.fq2("inv", q2))
+
+
+@pytest.mark.parametrize("group", ["g1", "g2"])
+def test_emulated_jacobian_doubling_chain(emu, orc, group):
+    """jac_dbl (window-table builder): 2^k P for k up to a full window, against the big-int model"""
+    if group == "g1":
+        F, fn, from_arr, limbs = P.F1, emu.emu_g1_jac_dbl_chain, P.g1_from_arr, 12
+        base = orc.g1_generate(0xE5, 1)[0]
+    else:
+        F, fn, from_arr, limbs = P.F2, emu.emu_g2_jac_dbl_chain, P.g2_from_arr, 24
+        g, _ = P.g2_to_arr((P.G2_X, P.G2_Y))
+        base = orc.g2_generate(g, 0xE6, 1)[0]
+    for k in (0, 1, 2, 13, 23):
+        out = np.zeros(limbs, dtype=np.uint64)
+        fn(_p32(base), C.c_uint32(k), _p32(out))
+        assert from_arr(out) == P.ec_mul(F, 1 << k, from_arr(base))

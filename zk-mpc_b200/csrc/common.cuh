@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 
@@ -59,7 +61,24 @@ struct DeviceInfo {
 int32_t enter(cudaStream_t* stream_out);
 const DeviceInfo* current_device_info();
 int current_device_index();      // index into the init list (per-device caches are keyed by it)
+int device_list_size();          // devices of the init list (0 before init)
 bool is_leader();
+
+// Multi-GPU entry points drive several devices from one host thread: a DeviceScope makes device `index`
+// of the init list the calling thread's current mpc_cuda device (and CUDA device) until it goes out of
+// scope, then restores the previous one.  stream() is the thread's own stream on that device.
+struct DeviceScope {
+    int saved;
+    int32_t rc;
+    cudaStream_t s = nullptr;
+    explicit DeviceScope(int index);
+    ~DeviceScope();
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+// cudaDeviceEnablePeerAccess between every ordered pair of the init list (idempotent, thread-safe);
+// fails with MPC_CUDA_ERR_CUDA when a pair cannot reach each other
+int32_t enable_peer_access();
 
 void count_launch();
 
@@ -75,9 +94,10 @@ struct ProfileScope {
 };
 
 // tuning knobs set through mpc_cuda_set_option (0 = automatic)
-extern int64_t g_opt_msm_window_bits;
-extern int64_t g_opt_msm_task_len;
-extern int64_t g_opt_profile;
+extern std::atomic<int64_t> g_opt_msm_window_bits;
+extern std::atomic<int64_t> g_opt_msm_task_len;
+extern std::atomic<int64_t> g_opt_msm_host_chunks;
+extern std::atomic<int64_t> g_opt_profile;
 
 inline cudaStream_t pick_stream(void* user, cudaStream_t mine) { return user ? (cudaStream_t)user : mine; }
 

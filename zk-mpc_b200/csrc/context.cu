@@ -29,8 +29,22 @@ static thread_local int t_dev_index = -1;       // index into g_devices
 static thread_local uint32_t t_party = 0, t_parties = 1;
 static thread_local cudaStream_t t_streams[64] = {};
 
+// Builds the device list in a local vector and publishes it only when every device passed, so a failed
+// attempt leaves nothing behind.  Once initialised, a request for a DIFFERENT explicit list is an error
+// (the library keeps per-device caches keyed by list index); NULL/0 or the same list is a no-op.
 static int32_t init_locked(const int32_t* devices, int32_t n_dev) {
-    if (g_inited) return MPC_CUDA_OK;
+    if (g_inited) {
+        if (devices && n_dev > 0) {
+            bool same = (size_t)n_dev == g_devices.size();
+            for (int i = 0; same && i < n_dev; i++) same = devices[i] == g_devices[i].cuda_device;
+            if (!same) {
+                set_error("mpc_cuda_init: already initialised with a different device list (%zu devices, first = CUDA %d)",
+                          g_devices.size(), g_devices.empty() ? -1 : g_devices[0].cuda_device);
+                return MPC_CUDA_ERR_ARG;
+            }
+        }
+        return MPC_CUDA_OK;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -45,12 +59,19 @@ static int32_t init_locked(const int32_t* devices, int32_t n_dev) {
                 set_error("device %d out of range (0..%d)", devices[i], count - 1);
                 return MPC_CUDA_ERR_ARG;
             }
+            for (int j = 0; j < i; j++) {
+                if (devices[j] == devices[i]) {
+                    set_error("device %d listed twice", devices[i]);
+                    return MPC_CUDA_ERR_ARG;
+                }
+            }
             ids.push_back(devices[i]);
         }
     } else {
         for (int i = 0; i < count; i++) ids.push_back(i);
     }
     if (ids.size() > 64) ids.resize(64);
+    std::vector<DeviceInfo> found;
     for (int id : ids) {
         cudaDeviceProp prop;
         MPC_CUDA_TRY(cudaGetDeviceProperties(&prop, id));
@@ -61,13 +82,14 @@ static int32_t init_locked(const int32_t* devices, int32_t n_dev) {
         DeviceInfo d;
         d.cuda_device = id;
         d.sm_count = prop.multiProcessorCount;
-        g_devices.push_back(d);
+        found.push_back(d);
         // keep freed scratch in the pool instead of returning it to the driver on every sync
         cudaMemPool_t pool;
         MPC_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, id));
         uint64_t threshold = UINT64_MAX;
         MPC_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     }
+    g_devices.swap(found);
     g_inited = true;
     return MPC_CUDA_OK;
 }
@@ -84,6 +106,72 @@ int32_t enter(cudaStream_t* stream_out) {
     return MPC_CUDA_OK;
 }
 
+int device_list_size() { return g_inited ? (int)g_devices.size() : 0; }
+
+DeviceScope::DeviceScope(int index) : saved(t_dev_index), rc(MPC_CUDA_OK) {
+    if (index < 0 || index >= (int)g_devices.size()) {
+        set_error("device index %d outside the init list of %zu devices", index, g_devices.size());
+        rc = MPC_CUDA_ERR_ARG;
+        return;
+    }
+    t_dev_index = index;
+    rc = enter(&s);
+}
+
+DeviceScope::~DeviceScope() {
+    t_dev_index = saved;
+    if (saved >= 0 && saved < (int)g_devices.size()) cudaSetDevice(g_devices[saved].cuda_device);
+}
+
+static bool g_peers_enabled = false;
+int32_t enable_peer_access() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    MPC_TRY(init_locked(nullptr, 0));
+    if (g_peers_enabled) return MPC_CUDA_OK;
+    int cur = 0;
+    MPC_CUDA_TRY(cudaGetDevice(&cur));
+    for (size_t a = 0; a < g_devices.size(); a++) {
+        MPC_CUDA_TRY(cudaSetDevice(g_devices[a].cuda_device));
+        for (size_t b = 0; b < g_devices.size(); b++) {
+            if (a == b) continue;
+            int can = 0;
+            MPC_CUDA_TRY(cudaDeviceCanAccessPeer(&can, g_devices[a].cuda_device, g_devices[b].cuda_device));
+            if (!can) {
+                cudaSetDevice(cur);
+                set_error("CUDA devices %d and %d have no peer access", g_devices[a].cuda_device, g_devices[b].cuda_device);
+                return MPC_CUDA_ERR_CUDA;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(g_devices[b].cuda_device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) {
+                cudaSetDevice(cur);
+                set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", g_devices[a].cuda_device, g_devices[b].cuda_device,
+                          cudaGetErrorString(e));
+                return MPC_CUDA_ERR_CUDA;
+            }
+        }
+    }
+    // stream-ordered scratch (cudaMallocAsync) is invisible to peers by default: open every default pool to
+    // every other device of the list, so peer copies and peer loads/stores work on scratch too
+    for (size_t a = 0; a < g_devices.size(); a++) {
+        cudaMemPool_t pool;
+        MPC_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g_devices[a].cuda_device));
+        std::vector<cudaMemAccessDesc> desc;
+        for (size_t b = 0; b < g_devices.size(); b++) {
+            if (a == b) continue;
+            cudaMemAccessDesc d = {};
+            d.location.type = cudaMemLocationTypeDevice;
+            d.location.id = g_devices[b].cuda_device;
+            d.flags = cudaMemAccessFlagsProtReadWrite;
+            desc.push_back(d);
+        }
+        if (!desc.empty()) MPC_CUDA_TRY(cudaMemPoolSetAccess(pool, desc.data(), desc.size()));
+    }
+    MPC_CUDA_TRY(cudaSetDevice(cur));
+    g_peers_enabled = true;
+    return MPC_CUDA_OK;
+}
+
 const DeviceInfo* current_device_info() {
     if (t_dev_index < 0 || t_dev_index >= (int)g_devices.size()) return nullptr;
     return &g_devices[t_dev_index];
@@ -91,7 +179,7 @@ const DeviceInfo* current_device_info() {
 
 int current_device_index() { return t_dev_index; }
 
-int64_t g_opt_profile = 0;
+std::atomic<int64_t> g_opt_profile{0};
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -105,7 +193,7 @@ static thread_local std::vector<Pending> t_pending;
 static thread_local std::map<std::string, std::pair<double, uint64_t>> t_totals;
 
 void profile_begin(const char* name, cudaStream_t s) {
-    if (!g_opt_profile) return;
+    if (!g_opt_profile.load(std::memory_order_relaxed)) return;
     Pending p;
     p.name = name;
     p.closed = false;
@@ -115,7 +203,7 @@ void profile_begin(const char* name, cudaStream_t s) {
 }
 
 void profile_end(const char* name, cudaStream_t s) {
-    if (!g_opt_profile) return;
+    if (!g_opt_profile.load(std::memory_order_relaxed)) return;
     for (size_t i = t_pending.size(); i-- > 0;) {
         if (!t_pending[i].closed && t_pending[i].name == name) {
             cudaEventRecord(t_pending[i].e1, s);
@@ -191,6 +279,9 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "msm_task_len")) {
         MPC_ARG_CHECK(value >= 0 && value <= (1 << 20));
         g_opt_msm_task_len = value;
+    } else if (!strcmp(name, "msm_host_chunks")) {
+        MPC_ARG_CHECK(value >= 0 && value <= 16);
+        g_opt_msm_host_chunks = value;
     } else {
         set_error("unknown option '%s'", name);
         return MPC_CUDA_ERR_ARG;

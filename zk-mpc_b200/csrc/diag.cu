@@ -21,6 +21,7 @@ __global__ void k_field_op(uint32_t op, const F* __restrict__ a, const F* __rest
         case 5: r = from_mont(x); break;
         case 6: r = to_mont(x); break;
         case 8: r = mul_narrow(x, y); break;
+        case 9: r = inv_euclid(x); break;
         default: r = sqr(x); break;
     }
     store_fe(out + i, r);
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(MB_THREADS) k_mb_mul(uint32_t iters, const F* 
 extern "C" {
 
 int32_t mpc_cuda_field_op(uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
-    MPC_ARG_CHECK(field <= 1 && op <= 8);
+    MPC_ARG_CHECK(field <= 1 && op <= 9);
     return field == 0 ? field_op<Fr>(op, a, b, out, n) : field_op<Fq>(op, a, b, out, n);
 }
 

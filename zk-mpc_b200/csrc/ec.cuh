@@ -163,3 +163,115 @@ HD XYZZ<F> xyzz_mul_small(const XYZZ<F>& q, uint64_t k) {
     }
     return acc;
 }
+
+// affine normal form through the binary-Euclid inversion: for the one-thread result emission
+template <class F>
+HD bool xyzz_to_affine_tail(const XYZZ<F>& p, F& ox, F& oy) {
+    if (p.is_inf()) { ox = F::zero(); oy = F::one(); return false; }
+    F t = inv_euclid(mul(p.zz, p.zzz));
+    ox = mul(p.x, mul(t, p.zzz));
+    oy = mul(p.y, mul(t, p.zz));
+    return true;
+}
+
+// Jacobian doubling for a = 0 (EFD dbl-2009-l, the formula of double_in_place,
+// short_weierstrass_jacobian.rs:557-600): 2M + 5S against XYZZ's 6M + 3S.  Used by the window-table
+// builder, whose cost is the 253 doublings per base.  Z = 0 stays Z = 0.
+template <class F>
+HD void jac_dbl(Jac<F>& p) {
+    F a = sqr(p.x);
+    F b = sqr(p.y);
+    F c = sqr(b);
+    F d = dbl(sub(sub(sqr(add(p.x, b)), a), c));
+    F e = add(dbl(a), a);
+    F f = sqr(e);
+    F z3 = dbl(mul(p.y, p.z));
+    F x3 = sub(f, dbl(d));
+    F c8 = dbl(dbl(dbl(c)));
+    p.y = sub(mul(e, sub(d, x3)), c8);
+    p.x = x3;
+    p.z = z3;
+}
+
+#if defined(__CUDACC__)
+// ---- warp-cooperative group law for the serial tails ----------------------------------------------------
+// The Horner combine of the window sums and the last few additions of an MSM are one dependent chain of
+// field products; a single thread pays the full carry-chain latency of every product (~1 us each).  Here
+// all lanes of a warp hold the same point and the independent products of one formula level are computed
+// by different lanes at once (SIMD lanes are free), then broadcast: a doubling is 3 product latencies
+// instead of 9, an addition 5 instead of 14.  Callers run these with a full, converged warp.
+template <class P>
+DEV Fp<P> warp_bcast(const Fp<P>& a, int src) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    return r;
+}
+template <class P>
+DEV Fp2<P> warp_bcast(const Fp2<P>& a, int src) {
+    Fp2<P> r;
+    r.c0 = warp_bcast(a.c0, src);
+    r.c1 = warp_bcast(a.c1, src);
+    return r;
+}
+
+// r[j] = a[j] * b[j] for j < K (K <= 4), product j computed by lane j, every lane receives all results
+template <int K, class F>
+DEV void warp_mul(F* r, const F* a, const F* b) {
+    const int lane = threadIdx.x & 31;
+    F x = a[0], y = b[0];
+#pragma unroll
+    for (int j = 1; j < K; j++)
+        if (lane == j) { x = a[j]; y = b[j]; }
+    F p = mul(x, y);
+#pragma unroll
+    for (int j = 0; j < K; j++) r[j] = warp_bcast(p, j);
+}
+
+template <class F>
+DEV void xyzz_dbl_warp(XYZZ<F>& p) {
+    if (p.is_inf()) return;                  // uniform across the warp: every lane holds the same point
+    F u = dbl(p.y);
+    F a1[2] = {u, p.x}, r1[2];
+    warp_mul<2>(r1, a1, a1);                 // v = u^2, xx = x^2
+    F v = r1[0], m = add(dbl(r1[1]), r1[1]);
+    F a2[4] = {u, p.x, m, v}, b2[4] = {v, v, m, p.zz}, r2[4];
+    warp_mul<4>(r2, a2, b2);                 // w = u v, s = x v, m^2, zz' = v zz
+    F w = r2[0], s = r2[1];
+    F x3 = sub(r2[2], dbl(s));
+    F a3[3] = {m, w, w}, b3[3] = {sub(s, x3), p.y, p.zzz}, r3[3];
+    warp_mul<3>(r3, a3, b3);                 // m (s - x3), w y, zzz' = w zzz
+    p.x = x3;
+    p.y = sub(r3[0], r3[1]);
+    p.zz = r2[3];
+    p.zzz = r3[2];
+}
+
+template <class F>
+DEV void xyzz_add_warp(XYZZ<F>& p, const XYZZ<F>& q) {
+    if (q.is_inf()) return;
+    if (p.is_inf()) { p = q; return; }
+    F a1[4] = {p.x, q.x, p.y, q.y}, b1[4] = {q.zz, p.zz, q.zzz, p.zzz}, r1[4];
+    warp_mul<4>(r1, a1, b1);                 // u1, u2, s1, s2
+    F pp = sub(r1[1], r1[0]);
+    F r = sub(r1[3], r1[2]);
+    if (pp.is_zero()) {
+        if (r.is_zero()) xyzz_dbl_warp(p);
+        else p = XYZZ<F>::infinity();
+        return;
+    }
+    F a2[4] = {pp, r, p.zz, p.zzz}, b2[4] = {pp, r, q.zz, q.zzz}, r2[4];
+    warp_mul<4>(r2, a2, b2);                 // p2, r^2, zz1 zz2, zzz1 zzz2
+    F p2 = r2[0];
+    F a3[3] = {pp, r1[0], r2[2]}, b3[3] = {p2, p2, p2}, r3[3];
+    warp_mul<3>(r3, a3, b3);                 // p3, q2 = u1 p2, zz3
+    F p3 = r3[0], q2 = r3[1];
+    F x3 = sub(sub(r2[1], p3), dbl(q2));
+    F a4[3] = {r, r1[2], r2[3]}, b4[3] = {sub(q2, x3), p3, p3}, r4[3];
+    warp_mul<3>(r4, a4, b4);                 // r (q2 - x3), s1 p3, zzz3
+    p.x = x3;
+    p.y = sub(r4[0], r4[1]);
+    p.zz = r3[2];
+    p.zzz = r4[2];
+}
+#endif

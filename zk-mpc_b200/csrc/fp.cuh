@@ -439,3 +439,62 @@ HD Fp<P> inv(const Fp<P>& a) {
     }
     return acc;
 }
+
+// Binary extended Euclid, the algorithm of the reference's `inverse` (ff/src/fields/macros.rs:389-443:
+// Guajardo-Kumar-Paar-Pelzl, u = a, v = p, b = R^2, c = 0 on plain integers), so a Montgomery input xR
+// yields x^-1 R.  About 2 log2(p) shift/subtract rounds of O(N) word operations: ~20x fewer instructions
+// than the Fermat ladder above, but data-dependent control flow — meant for single-thread tails (result
+// normalisation) where latency, not divergence, is what matters.  0 -> 0.
+namespace fp_detail {
+template <int N> HD void shr1(uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[N - 1] >>= 1;
+}
+template <int N> HD bool is_one(const uint32_t* a) {
+    uint32_t acc = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < N; i++) acc |= a[i];
+    return acc == 0;
+}
+template <int N> HD bool less_than(const uint32_t* a, const uint32_t* b) {      // a < b
+    ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) ptx::subc_cc(a[i], b[i]);
+    return ptx::subc(0, 0) != 0;
+}
+template <int N> HD void sub_raw(uint32_t* a, const uint32_t* b) {              // a -= b, a >= b
+    a[0] = ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) a[i] = ptx::subc_cc(a[i], b[i]);
+    a[N - 1] = ptx::subc(a[N - 1], b[N - 1]);
+}
+// b = b / 2 mod p for b in [0, p): b even -> b >> 1, else (b + p) >> 1 (p has spare top bits)
+template <class P> HD void half_mod(uint32_t* b) {
+    constexpr int N = P::N;
+    if (b[0] & 1u) {
+        b[0] = ptx::add_cc(b[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) b[i] = ptx::addc_cc(b[i], P::mod(i));
+        b[N - 1] = ptx::addc(b[N - 1], P::mod(N - 1));
+    }
+    shr1<N>(b);
+}
+}  // namespace fp_detail
+
+template <class P>
+HD Fp<P> inv_euclid(const Fp<P>& a) {
+    using namespace fp_detail;
+    constexpr int N = P::N;
+    if (a.is_zero()) return Fp<P>::zero();
+    Fp<P> u = a, v = Fp<P>::modulus(), b, c = Fp<P>::zero();
+#pragma unroll
+    for (int i = 0; i < N; i++) b.v[i] = P::r2(i);
+    while (!is_one<N>(u.v) && !is_one<N>(v.v)) {
+        while (!(u.v[0] & 1u)) { shr1<N>(u.v); half_mod<P>(b.v); }
+        while (!(v.v[0] & 1u)) { shr1<N>(v.v); half_mod<P>(c.v); }
+        if (less_than<N>(v.v, u.v)) { sub_raw<N>(u.v, v.v); b = sub(b, c); }
+        else { sub_raw<N>(v.v, u.v); c = sub(c, b); }
+    }
+    return is_one<N>(u.v) ? b : c;
+}

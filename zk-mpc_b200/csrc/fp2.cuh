@@ -62,3 +62,14 @@ HD Fp2<P> inv(const Fp2<P>& a) {
     r.c1 = neg(mul(a.c1, ni));
     return r;
 }
+
+// same value through the binary-Euclid base-field inversion (single-thread tails, see fp.cuh)
+template <class P>
+HD Fp2<P> inv_euclid(const Fp2<P>& a) {
+    Fp<P> norm = add(sqr(a.c0), mul5(sqr(a.c1)));
+    Fp<P> ni = inv_euclid(norm);
+    Fp2<P> r;
+    r.c0 = mul(a.c0, ni);
+    r.c1 = neg(mul(a.c1, ni));
+    return r;
+}

@@ -1,4 +1,5 @@
 // Share MSM on G1 / G2: signed-digit Pippenger bucket method, one pipeline of kernels per call.
+// Implementation header: included by msm_g1.cu (F = Fq) and msm_g2.cu (F = Fq2), which export the C ABI.
 //
 // Replaces   VariableBaseMSM::multi_scalar_mul  arkworks/algebra/ec/src/msm/variable_base.rs:12-106
 //            AffineCurve::multi_scalar_mul       arkworks/algebra/ec/src/lib.rs:305-314  (into_repr of every scalar)
@@ -7,30 +8,26 @@
 // reference's serial loop (signed digits, XYZZ buckets, sorted point lists) and still returns the
 // bit-identical point.
 //
-// Pipeline (all on one stream, no host synchronisation until the result is read):
-//   k_digits          Montgomery -> canonical scalar, signed c-bit digits          n x 32 B in, nwin x n x 4 B out
-//   k_hist            per (window, chunk) bucket histogram in shared memory
-//   k_scan_window     bucket start offsets + per-chunk scatter cursors
-//   k_task_scan / k_build_tasks   cut buckets into tasks of <= task_len points (load balance)
-//   k_scatter         counting sort: point indices grouped by bucket
-//   k_accumulate      HOT: each thread pulls tasks and sums its points with XYZZ mixed additions
-//   k_finalize_*      join the partial sums of buckets that were split
-//   k_bucket_reduce   Σ b·B_b per window by chunked running sums, k_window_sum, k_horner
-#include <mutex>
-#include <unordered_map>
+// Pipeline (all on one stream, no host synchronisation until the result is read).  The points may arrive in
+// several CHUNKS (point ranges) that add into the same bucket set, so a host-buffer call overlaps the PCIe
+// copy of chunk j+1 with the sort and accumulation of chunk j:
+//   per chunk   k_digits          Montgomery -> canonical scalar, signed c-bit digits
+//               k_hist1/k_scan1/k_scatter1/k_sort2   two-level counting sort by bucket
+//               k_task_*          cut buckets into tasks of <= task_len points (load balance)
+//               k_accumulate      HOT: each thread pulls tasks and sums its points with XYZZ mixed additions
+//               k_finalize_*      join the partial sums of buckets that were split
+//   once        k_bucket_reduce   Σ b·B_b per window by chunked running sums, k_window_sum
+//               k_horner          warp-cooperative Σ_w 2^(cw) S_w        k_emit   affine / Jacobian result
+#pragma once
+#include <algorithm>
 
 #include "common.cuh"
 #include "ec.cuh"
 #include "msm_digits.cuh"
+#include "msm_registry.cuh"
 
 using namespace mpc;
 using Fq2 = Fp2<consts::FqParams>;
-
-namespace mpc {
-// tuning knobs (mpc_cuda_set_option); 0 = automatic
-int64_t g_opt_msm_window_bits = 0;
-int64_t g_opt_msm_task_len = 0;
-}  // namespace mpc
 
 namespace {
 
@@ -80,13 +77,13 @@ DEV void store_pod(T* p, const T& v) {
 
 // ---- plan -------------------------------------------------------------------------------------------
 struct Plan {
-    size_t n;                    // scalars of this call
-    size_t sn;                   // entries per sorted window: n, or nwin*n when all windows share one bucket set
+    size_t n;                    // scalars of the whole MSM
+    size_t cap;                  // longest chunk (point range) the scratch is sized for
+    size_t sn_cap;               // entries per sorted window of a longest chunk: cap, or nwin*cap with a table
     uint32_t snwin;              // bucket sets: nwin, or 1 with a precomputed table of 2^(c*w)*P
     uint32_t c, nwin, nb;        // window bits, windows, buckets per window = 2^(c-1)
     uint32_t hi_bits, lo_bits;   // bucket id = (hi << lo_bits) | lo: level-1 partitions / level-2 bins
     uint32_t chunks;             // level-1 sort chunks per window
-    size_t chunk_len;
     uint32_t task_len;           // max points per accumulate task
     size_t max_tasks;
     uint32_t scan_blocks;        // blocks of the task scan (SCAN_ITEMS buckets each)
@@ -98,16 +95,17 @@ constexpr uint32_t HI_BITS_MAX = 11;            // <= 2048 write streams per CTA
 constexpr uint32_t SCAN_PER_THREAD = 8;
 constexpr uint32_t SCAN_ITEMS = 1024 * SCAN_PER_THREAD;
 
-uint32_t log2_ceil(size_t x) {
+inline uint32_t log2_ceil(size_t x) {
     uint32_t l = 0;
     while (((size_t)1 << l) < x) l++;
     return l;
 }
 
-Plan make_plan(size_t n, int sm_count, uint32_t table_c) {
+inline Plan make_plan(size_t n, size_t cap, int sm_count, uint32_t table_c) {
     Plan p;
     p.n = n;
-    int64_t c = table_c ? table_c : g_opt_msm_window_bits;
+    p.cap = cap;
+    int64_t c = table_c ? table_c : g_opt_msm_window_bits.load(std::memory_order_relaxed);
     if (c <= 0) {
         // madds = n * windows against bucket work ~ windows * 2^(c-1) * 3; measured on B200 with
         // tools/tune_msm.py (2^24: c = 20, 2^20: c = 17, 2^16: c = 15).  Widths whose top window holds a
@@ -124,16 +122,15 @@ Plan make_plan(size_t n, int sm_count, uint32_t table_c) {
     p.hi_bits = kb < HI_BITS_MAX ? kb : HI_BITS_MAX;
     p.lo_bits = kb - p.hi_bits;
     p.snwin = table_c ? 1 : p.nwin;
-    p.sn = table_c ? n * p.nwin : n;
+    p.sn_cap = table_c ? cap * p.nwin : cap;
     uint32_t want = (uint32_t)((4 * sm_count + p.snwin - 1) / p.snwin);
-    size_t by_len = (p.sn + 8191) / 8192;
+    size_t by_len = (p.sn_cap + 8191) / 8192;
     p.chunks = (uint32_t)(by_len < want ? by_len : want);
     if (p.chunks < 1) p.chunks = 1;
-    p.chunk_len = (p.sn + p.chunks - 1) / p.chunks;
-    int64_t tl = g_opt_msm_task_len;
+    int64_t tl = g_opt_msm_task_len.load(std::memory_order_relaxed);
     if (tl <= 0) {
         // enough tasks to balance the resident threads, but not so short that joins dominate
-        size_t entries = n * (size_t)p.nwin;
+        size_t entries = cap * (size_t)p.nwin;
         size_t resident = (size_t)sm_count * 384;
         tl = (int64_t)(entries / (resident * 8));
         if (tl < 32) tl = 32;
@@ -141,7 +138,7 @@ Plan make_plan(size_t n, int sm_count, uint32_t table_c) {
     }
     p.task_len = (uint32_t)tl;
     size_t nbuckets = (size_t)p.snwin * p.nb;
-    p.max_tasks = n * (size_t)p.nwin / p.task_len + nbuckets + 1;
+    p.max_tasks = cap * (size_t)p.nwin / p.task_len + nbuckets + 1;
     p.scan_blocks = (uint32_t)((nbuckets + SCAN_ITEMS - 1) / SCAN_ITEMS);
     // bucket-reduce chunk: short chunks (more threads, shorter serial chains) while the grid stays small,
     // longer ones once there are enough chunks to fill the machine
@@ -351,7 +348,8 @@ __global__ void __launch_bounds__(1024) k_task_sums(const uint32_t* __restrict__
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-// (b) single block: exclusive scan of the block totals in place; counters[0] = number of tasks
+// (b) single block: exclusive scan of the block totals in place; counters[0] = number of tasks, the claim
+// counter and the split-bucket list lengths restart at zero (one counter block serves every chunk)
 __global__ void __launch_bounds__(1024) k_task_offsets(uint32_t* __restrict__ block_sums, uint32_t nblocks,
                                                        uint32_t* __restrict__ counters) {
     __shared__ uint32_t sm[1024];
@@ -367,7 +365,7 @@ __global__ void __launch_bounds__(1024) k_task_offsets(uint32_t* __restrict__ bl
         block_sums[b] = run;
         run += t;
     }
-    if (threadIdx.x == 0) counters[0] = total;
+    if (threadIdx.x == 0) { counters[0] = total; counters[1] = 0; counters[2] = 0; counters[3] = 0; }
 }
 
 // (c) task = (first slot in the window's sorted list, length, bucket, bucket-has-a-single-task)
@@ -406,13 +404,15 @@ __global__ void __launch_bounds__(1024) k_build_tasks(const uint32_t* __restrict
 // Every thread repeatedly claims a task (a run of <= task_len sorted entries of one bucket) and adds the
 // referenced affine bases into an XYZZ accumulator.  The claim is folded into the point loop, so the
 // lanes of a warp stay converged on the mixed addition whatever the task lengths are.
+// merge != 0 (second and later chunks of a streamed MSM): a bucket's accumulator starts from the value the
+// earlier chunks left in it instead of infinity — no extra field products.
 template <class F>
 __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(const Affine<F>* __restrict__ bases,
                                                             const uint32_t* __restrict__ sorted, size_t n, uint32_t nb,
                                                             const uint4* __restrict__ tasks,
                                                             uint32_t* __restrict__ counters,
                                                             XYZZ<F>* __restrict__ buckets,
-                                                            XYZZ<F>* __restrict__ partials) {
+                                                            XYZZ<F>* __restrict__ partials, uint32_t merge) {
     const uint32_t total = counters[0];
     XYZZ<F> acc = XYZZ<F>::infinity();
     uint32_t k = 0, len = 0, task_id = 0;
@@ -427,7 +427,8 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(cons
             k = 0;
             len = t.y;
             list = sorted + (size_t)(t.z / nb) * n + t.x;
-            acc = XYZZ<F>::infinity();
+            if (merge && t.w) acc = load_pod(buckets + t.z);
+            else acc = XYZZ<F>::infinity();
         }
         uint32_t e = __ldg(list + k);
         k++;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_finalize_small(const uint32_t* 
                                                                 const uint32_t* __restrict__ bucket_size,
                                                                 const uint32_t* __restrict__ task_start,
                                                                 uint32_t task_len, const XYZZ<F>* __restrict__ partials,
-                                                                XYZZ<F>* __restrict__ buckets) {
+                                                                XYZZ<F>* __restrict__ buckets, uint32_t merge) {
     uint32_t count = counters[2];
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
@@ -453,6 +454,10 @@ __global__ void __launch_bounds__(ACC_THREADS) k_finalize_small(const uint32_t* 
         XYZZ<F> acc = load_pod(partials + ts);
         for (uint32_t k = 1; k < nt; k++) {
             XYZZ<F> q = load_pod(partials + ts + k);
+            xyzz_add(acc, q);
+        }
+        if (merge) {
+            XYZZ<F> q = load_pod(buckets + g);
             xyzz_add(acc, q);
         }
         store_pod(buckets + g, acc);
@@ -466,7 +471,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_finalize_big(const uint32_t* __
                                                               const uint32_t* __restrict__ bucket_size,
                                                               const uint32_t* __restrict__ task_start,
                                                               uint32_t task_len, const XYZZ<F>* __restrict__ partials,
-                                                              XYZZ<F>* __restrict__ buckets) {
+                                                              XYZZ<F>* __restrict__ buckets, uint32_t merge) {
     extern __shared__ uint4 sm_raw[];
     XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(sm_raw);
     uint32_t count = counters[3];
@@ -474,6 +479,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_finalize_big(const uint32_t* __
         uint32_t g = big_list[i];
         uint32_t nt = (bucket_size[g] + task_len - 1) / task_len, ts = task_start[g];
         XYZZ<F> acc = XYZZ<F>::infinity();
+        if (merge && threadIdx.x == 0) acc = load_pod(buckets + g);
         for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
             XYZZ<F> q = load_pod(partials + ts + k);
             xyzz_add(acc, q);
@@ -548,33 +554,38 @@ __global__ void __launch_bounds__(ACC_THREADS) k_window_sum(const XYZZ<F>* __res
     }
 }
 
-// Σ_w 2^(c·w)·S_w, high to low (variable_base.rs:92-105)
+// Σ_w 2^(c·w)·S_w, high to low (variable_base.rs:92-105): one warp, every lane holds the accumulator and
+// the independent products of each doubling / addition run on different lanes (ec.cuh, warp-cooperative
+// group law): 3 product latencies per doubling instead of 9.
 template <class F>
-__global__ void k_horner(const XYZZ<F>* __restrict__ window_sum, uint32_t nwin, uint32_t c, XYZZ<F>* __restrict__ out) {
-    if (blockIdx.x || threadIdx.x) return;
+__global__ void __launch_bounds__(32) k_horner(const XYZZ<F>* __restrict__ window_sum, uint32_t nwin, uint32_t c,
+                                               XYZZ<F>* __restrict__ out) {
     XYZZ<F> acc = load_pod(window_sum + nwin - 1);
     for (uint32_t w = nwin - 1; w-- > 0;) {
-        for (uint32_t k = 0; k < c; k++) xyzz_dbl(acc);
+        for (uint32_t k = 0; k < c; k++) xyzz_dbl_warp(acc);
         XYZZ<F> q = load_pod(window_sum + w);
-        xyzz_add(acc, q);
+        xyzz_add_warp(acc, q);
     }
-    store_pod(out, acc);
+    if (threadIdx.x == 0) store_pod(out, acc);
 }
 
 // ---- result emission ----------------------------------------------------------------------------------
-// mode 0: affine x|y (2 F) followed by one 32-bit infinity flag;  mode 1: Jacobian x|y|z (3 F)
+// mode 0: affine x|y (2 F) followed by one 32-bit infinity flag;  mode 1: Jacobian x|y|z (3 F).
+// One warp: the additions are lane-parallel, the inversion is the binary-Euclid one (same data on every
+// lane, so no divergence), ~20x shorter than the Fermat ladder on a single dependent chain.
 template <class F>
-__global__ void k_emit(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t mode, uint32_t* __restrict__ out) {
-    if (blockIdx.x || threadIdx.x) return;
+__global__ void __launch_bounds__(32) k_emit(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t mode,
+                                             uint32_t* __restrict__ out) {
     XYZZ<F> acc = XYZZ<F>::infinity();
     for (uint32_t i = 0; i < count; i++) {
         XYZZ<F> q = load_pod(in + i);
-        xyzz_add(acc, q);
+        xyzz_add_warp(acc, q);
     }
+    if (threadIdx.x) return;
     constexpr int N = sizeof(F) / 4;
     if (mode == 0) {
         F x, y;
-        bool finite = xyzz_to_affine(acc, x, y);
+        bool finite = xyzz_to_affine_tail(acc, x, y);
         const uint32_t *px = reinterpret_cast<const uint32_t*>(&x), *py = reinterpret_cast<const uint32_t*>(&y);
         for (int i = 0; i < N; i++) { out[i] = px[i]; out[N + i] = py[i]; }
         out[2 * N] = finite ? 0u : 1u;
@@ -640,7 +651,139 @@ struct TableRef {
     size_t stride = 0, offset = 0;
 };
 
-// result (one XYZZ on the device) = Σ scalars[i] * bases[i]
+// One MSM in flight: begin() sizes the scratch for chunks of <= cap points, chunk() sorts and accumulates
+// one point range into the shared buckets, finish() reduces them to one XYZZ point.
+template <class F>
+struct MsmJob {
+    Plan p;
+    cudaStream_t s = nullptr;
+    const DeviceInfo* dev = nullptr;
+    bool use_table = false;
+    TableRef tbl;
+    size_t done = 0;             // points consumed so far
+    uint32_t nchunks = 0;
+    Scratch s_digits, s_sorted, s_pairs, s_hist, s_part, s_bstart, s_bsize, s_tstart, s_bsums, s_tasks, s_small, s_big,
+        s_cnt, s_buckets, s_partials, s_chunk, s_wpart, s_wsum;
+    uint32_t *digits, *sorted, *hist, *part_start, *bstart, *bsize, *tstart, *bsums, *small_list, *big_list, *counters;
+    uint2* pairs;
+    uint4* tasks;
+    XYZZ<F>*buckets, *partials, *chunk_res, *wpart, *wsum;
+    size_t nbuckets = 0;
+    int acc_blocks = 1;
+
+    int32_t begin(size_t n, size_t cap, cudaStream_t stream, const TableRef* t) {
+        s = stream;
+        dev = current_device_info();
+        use_table = t && t->table;
+        if (use_table) tbl = *t;
+        MPC_ARG_CHECK(n < ((size_t)1 << 31) && cap >= 1 && cap <= n);
+        p = make_plan(n, cap, dev->sm_count, use_table ? tbl.c : 0);
+        nbuckets = (size_t)p.snwin * p.nb;
+        MPC_ARG_CHECK(p.sn_cap < ((size_t)1 << 31) && (!use_table || (size_t)p.nwin * tbl.stride < ((size_t)1 << 31)));
+        MPC_ARG_CHECK(nbuckets < ((size_t)1 << 31) && (size_t)p.nwin * cap / p.task_len + nbuckets < ((size_t)1 << 32));
+        const uint32_t hbins = 1u << p.hi_bits;
+        MPC_TRY(s_digits.alloc(&digits, (size_t)p.nwin * cap, s));
+        MPC_TRY(s_sorted.alloc(&sorted, (size_t)p.nwin * cap, s));
+        MPC_TRY(s_pairs.alloc(&pairs, (size_t)p.nwin * cap, s));
+        MPC_TRY(s_hist.alloc(&hist, (size_t)p.snwin * p.chunks * hbins, s));
+        MPC_TRY(s_part.alloc(&part_start, (size_t)p.snwin * (hbins + 1), s));
+        MPC_TRY(s_bstart.alloc(&bstart, nbuckets, s));
+        MPC_TRY(s_bsize.alloc(&bsize, nbuckets, s));
+        MPC_TRY(s_tstart.alloc(&tstart, nbuckets, s));
+        MPC_TRY(s_bsums.alloc(&bsums, p.scan_blocks, s));
+        MPC_TRY(s_tasks.alloc(&tasks, p.max_tasks, s));
+        MPC_TRY(s_small.alloc(&small_list, nbuckets, s));
+        MPC_TRY(s_big.alloc(&big_list, nbuckets, s));
+        MPC_TRY(s_cnt.alloc(&counters, 8, s));
+        MPC_TRY(s_buckets.alloc(&buckets, nbuckets, s));
+        MPC_TRY(s_partials.alloc(&partials, p.max_tasks, s));
+        MPC_TRY(s_chunk.alloc(&chunk_res, (size_t)p.snwin * p.red_t, s));
+        MPC_TRY(s_wpart.alloc(&wpart, (size_t)p.snwin * p.sum_parts, s));
+        MPC_TRY(s_wsum.alloc(&wsum, p.snwin, s));
+        MPC_CUDA_TRY(cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), s));      // all-zero = infinity
+        MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F>, ACC_THREADS, 0));
+        if (acc_blocks < 1) acc_blocks = 1;
+        MPC_TRY(allow_smem(k_finalize_big<F>, ACC_THREADS * sizeof(XYZZ<F>)));
+        MPC_TRY(allow_smem(k_window_sum<F>, ACC_THREADS * sizeof(XYZZ<F>)));
+        return MPC_CUDA_OK;
+    }
+
+    // bases / inf / scalars: device pointers to this chunk's `len` points (bases unused with a table)
+    int32_t chunk(const Affine<F>* bases, const uint8_t* inf, const Fr* scalars, size_t len) {
+        if (len == 0) return MPC_CUDA_OK;
+        MPC_ARG_CHECK(len <= p.cap && done + len <= p.n);
+        const uint32_t hbins = 1u << p.hi_bits, lbins = 1u << p.lo_bits;
+        const size_t sn = use_table ? len * p.nwin : len;
+        const size_t chunk_len = (sn + p.chunks - 1) / p.chunks;
+        const uint32_t merge = nchunks ? 1u : 0u;
+        profile_begin("msm_sort", s);
+        // digits[w*len + i]: with a table the flat array IS one window of nwin*len entries
+        k_digits<<<grid_for(len, 256, 8), 256, 0, s>>>(scalars, inf, len, p.c, p.nwin, digits);
+        MPC_KERNEL_CHECK();
+        dim3 grid1(p.chunks, p.snwin);
+        k_hist1<<<grid1, SORT_THREADS, hbins * sizeof(uint32_t), s>>>(digits, sn, p.lo_bits, hbins, chunk_len, hist);
+        MPC_KERNEL_CHECK();
+        k_scan1<<<p.snwin, 1024, 0, s>>>(hist, p.chunks, hbins, part_start);
+        MPC_KERNEL_CHECK();
+        k_scatter1<<<grid1, SORT_THREADS, hbins * sizeof(uint32_t), s>>>(digits, sn, p.lo_bits, hbins, chunk_len, hist,
+                                                                        pairs, len, use_table ? tbl.stride : 0,
+                                                                        use_table ? tbl.offset + done : 0);
+        MPC_KERNEL_CHECK();
+        k_sort2<<<dim3(hbins, p.snwin), SORT2_THREADS, (lbins + SORT2_THREADS) * sizeof(uint32_t), s>>>(
+            pairs, part_start, sn, p.lo_bits, hbins, sorted, bstart, bsize);
+        MPC_KERNEL_CHECK();
+        k_task_sums<<<p.scan_blocks, 1024, 0, s>>>(bsize, nbuckets, p.task_len, bsums);
+        MPC_KERNEL_CHECK();
+        k_task_offsets<<<1, 1024, 0, s>>>(bsums, p.scan_blocks, counters);
+        MPC_KERNEL_CHECK();
+        k_build_tasks<<<p.scan_blocks, 1024, 0, s>>>(bstart, bsize, bsums, nbuckets, p.task_len, tasks, tstart,
+                                                     small_list, big_list, counters);
+        MPC_KERNEL_CHECK();
+        profile_end("msm_sort", s);
+
+        profile_begin("msm_accumulate", s);
+        k_accumulate<F><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(
+            use_table ? (const Affine<F>*)tbl.table : bases, sorted, sn, p.nb, tasks, counters, buckets, partials, merge);
+        MPC_KERNEL_CHECK();
+        profile_end("msm_accumulate", s);
+
+        profile_begin("msm_reduce", s);
+        k_finalize_small<F><<<dev->sm_count * 2, ACC_THREADS, 0, s>>>(small_list, counters, bsize, tstart, p.task_len,
+                                                                      partials, buckets, merge);
+        MPC_KERNEL_CHECK();
+        k_finalize_big<F><<<dev->sm_count, ACC_THREADS, ACC_THREADS * sizeof(XYZZ<F>), s>>>(
+            big_list, counters, bsize, tstart, p.task_len, partials, buckets, merge);
+        MPC_KERNEL_CHECK();
+        profile_end("msm_reduce", s);
+        done += len;
+        nchunks++;
+        return MPC_CUDA_OK;
+    }
+
+    int32_t finish(XYZZ<F>* result) {
+        profile_begin("msm_reduce", s);
+        const size_t tree_smem = ACC_THREADS * sizeof(XYZZ<F>);
+        uint32_t red_threads = p.snwin * p.red_t;
+        k_bucket_reduce<F><<<(red_threads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(buckets, p.snwin, p.nb,
+                                                                                                p.red_m, p.red_t, chunk_res);
+        MPC_KERNEL_CHECK();
+        if (p.sum_parts == 1) {
+            k_window_sum<F><<<dim3(1, p.snwin), ACC_THREADS, tree_smem, s>>>(chunk_res, p.red_t, p.red_t, wsum);
+            MPC_KERNEL_CHECK();
+        } else {
+            k_window_sum<F><<<dim3(p.sum_parts, p.snwin), ACC_THREADS, tree_smem, s>>>(chunk_res, p.red_t, 1024, wpart);
+            MPC_KERNEL_CHECK();
+            k_window_sum<F><<<dim3(1, p.snwin), ACC_THREADS, tree_smem, s>>>(wpart, p.sum_parts, p.sum_parts, wsum);
+            MPC_KERNEL_CHECK();
+        }
+        k_horner<F><<<1, 32, 0, s>>>(wsum, p.snwin, p.c, result);
+        MPC_KERNEL_CHECK();
+        profile_end("msm_reduce", s);
+        return MPC_CUDA_OK;
+    }
+};
+
+// result (one XYZZ on the device) = Σ scalars[i] * bases[i], everything already resident
 template <class F>
 int32_t msm_run(const Affine<F>* bases, const uint8_t* inf, const Fr* scalars, size_t n, XYZZ<F>* result,
                 cudaStream_t s, const TableRef* tbl = nullptr) {
@@ -648,168 +791,70 @@ int32_t msm_run(const Affine<F>* bases, const uint8_t* inf, const Fr* scalars, s
         MPC_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(XYZZ<F>), s));
         return MPC_CUDA_OK;
     }
-    MPC_ARG_CHECK(n < ((size_t)1 << 31));
-    const DeviceInfo* dev = current_device_info();
-    const bool use_table = tbl && tbl->table;
-    Plan p = make_plan(n, dev->sm_count, use_table ? tbl->c : 0);
-    const size_t sn = p.sn;
-    const uint32_t snwin = p.snwin;
-    size_t nbuckets = (size_t)snwin * p.nb;
-    MPC_ARG_CHECK(sn < ((size_t)1 << 31) && (!use_table || (size_t)p.nwin * tbl->stride < ((size_t)1 << 31)));
-    MPC_ARG_CHECK(nbuckets < ((size_t)1 << 31) && (size_t)p.nwin * n / p.task_len + nbuckets < ((size_t)1 << 32));
-
-    Scratch s_digits, s_sorted, s_pairs, s_hist, s_part, s_bstart, s_bsize, s_tstart, s_bsums, s_tasks, s_small, s_big,
-        s_cnt, s_buckets, s_partials, s_chunk, s_wpart, s_wsum;
-    uint32_t *digits, *sorted, *hist, *part_start, *bstart, *bsize, *tstart, *bsums, *small_list, *big_list, *counters;
-    uint2* pairs;
-    uint4* tasks;
-    XYZZ<F>*buckets, *partials, *chunk_res, *wpart, *wsum;
-    const uint32_t hbins = 1u << p.hi_bits, lbins = 1u << p.lo_bits;
-    MPC_TRY(s_digits.alloc(&digits, (size_t)p.nwin * n, s));
-    MPC_TRY(s_sorted.alloc(&sorted, (size_t)p.nwin * n, s));
-    MPC_TRY(s_pairs.alloc(&pairs, (size_t)p.nwin * n, s));
-    MPC_TRY(s_hist.alloc(&hist, (size_t)snwin * p.chunks * hbins, s));
-    MPC_TRY(s_part.alloc(&part_start, (size_t)snwin * (hbins + 1), s));
-    MPC_TRY(s_bstart.alloc(&bstart, nbuckets, s));
-    MPC_TRY(s_bsize.alloc(&bsize, nbuckets, s));
-    MPC_TRY(s_tstart.alloc(&tstart, nbuckets, s));
-    MPC_TRY(s_bsums.alloc(&bsums, p.scan_blocks, s));
-    MPC_TRY(s_tasks.alloc(&tasks, p.max_tasks, s));
-    MPC_TRY(s_small.alloc(&small_list, nbuckets, s));
-    MPC_TRY(s_big.alloc(&big_list, nbuckets, s));
-    MPC_TRY(s_cnt.alloc(&counters, 8, s));
-    MPC_TRY(s_buckets.alloc(&buckets, nbuckets, s));
-    MPC_TRY(s_partials.alloc(&partials, p.max_tasks, s));
-    MPC_TRY(s_chunk.alloc(&chunk_res, (size_t)snwin * p.red_t, s));
-    MPC_TRY(s_wpart.alloc(&wpart, (size_t)snwin * p.sum_parts, s));
-    MPC_TRY(s_wsum.alloc(&wsum, snwin, s));
-
     ProfileScope prof_total("msm_total", s);
-    profile_begin("msm_sort", s);
-    MPC_CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(uint32_t), s));
-    MPC_CUDA_TRY(cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), s));      // all-zero = infinity
-
-    // digits[w*n + i]: with a table the flat array IS one window of nwin*n entries
-    k_digits<<<grid_for(n, 256, 8), 256, 0, s>>>(scalars, inf, n, p.c, p.nwin, digits);
-    MPC_KERNEL_CHECK();
-
-    dim3 grid1(p.chunks, snwin);
-    k_hist1<<<grid1, SORT_THREADS, hbins * sizeof(uint32_t), s>>>(digits, sn, p.lo_bits, hbins, p.chunk_len, hist);
-    MPC_KERNEL_CHECK();
-    k_scan1<<<snwin, 1024, 0, s>>>(hist, p.chunks, hbins, part_start);
-    MPC_KERNEL_CHECK();
-    k_scatter1<<<grid1, SORT_THREADS, hbins * sizeof(uint32_t), s>>>(digits, sn, p.lo_bits, hbins, p.chunk_len, hist, pairs,
-                                                                    n, use_table ? tbl->stride : 0,
-                                                                    use_table ? tbl->offset : 0);
-    MPC_KERNEL_CHECK();
-    k_sort2<<<dim3(hbins, snwin), SORT2_THREADS, (lbins + SORT2_THREADS) * sizeof(uint32_t), s>>>(pairs, part_start, sn, p.lo_bits, hbins, sorted,
-                                                                             bstart, bsize);
-    MPC_KERNEL_CHECK();
-    k_task_sums<<<p.scan_blocks, 1024, 0, s>>>(bsize, nbuckets, p.task_len, bsums);
-    MPC_KERNEL_CHECK();
-    k_task_offsets<<<1, 1024, 0, s>>>(bsums, p.scan_blocks, counters);
-    MPC_KERNEL_CHECK();
-    k_build_tasks<<<p.scan_blocks, 1024, 0, s>>>(bstart, bsize, bsums, nbuckets, p.task_len, tasks, tstart, small_list,
-                                                 big_list, counters);
-    MPC_KERNEL_CHECK();
-    profile_end("msm_sort", s);
-
-    int acc_blocks = 0;
-    MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F>, ACC_THREADS, 0));
-    if (acc_blocks < 1) acc_blocks = 1;
-    profile_begin("msm_accumulate", s);
-    k_accumulate<F><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(
-        use_table ? (const Affine<F>*)tbl->table : bases, sorted, sn, p.nb, tasks, counters, buckets, partials);
-    MPC_KERNEL_CHECK();
-    profile_end("msm_accumulate", s);
-    profile_begin("msm_reduce", s);
-
-    k_finalize_small<F><<<dev->sm_count * 2, ACC_THREADS, 0, s>>>(small_list, counters, bsize, tstart, p.task_len,
-                                                                  partials, buckets);
-    MPC_KERNEL_CHECK();
-    size_t tree_smem = ACC_THREADS * sizeof(XYZZ<F>);
-    MPC_TRY(allow_smem(k_finalize_big<F>, tree_smem));
-    MPC_TRY(allow_smem(k_window_sum<F>, tree_smem));
-    k_finalize_big<F><<<dev->sm_count, ACC_THREADS, tree_smem, s>>>(big_list, counters, bsize, tstart, p.task_len,
-                                                                    partials, buckets);
-    MPC_KERNEL_CHECK();
-
-    uint32_t red_threads = snwin * p.red_t;
-    k_bucket_reduce<F><<<(red_threads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(buckets, snwin, p.nb,
-                                                                                            p.red_m, p.red_t, chunk_res);
-    MPC_KERNEL_CHECK();
-    k_window_sum<F><<<dim3(p.sum_parts, snwin), ACC_THREADS, tree_smem, s>>>(chunk_res, p.red_t, 1024, wpart);
-    MPC_KERNEL_CHECK();
-    k_window_sum<F><<<dim3(1, snwin), ACC_THREADS, tree_smem, s>>>(wpart, p.sum_parts, p.sum_parts, wsum);
-    MPC_KERNEL_CHECK();
-    k_horner<F><<<1, 32, 0, s>>>(wsum, snwin, p.c, result);
-    MPC_KERNEL_CHECK();
-    profile_end("msm_reduce", s);
-    return MPC_CUDA_OK;
+    MsmJob<F> job;
+    MPC_TRY(job.begin(n, n, s, tbl));
+    MPC_TRY(job.chunk(bases, inf, scalars, n));
+    return job.finish(result);
 }
 
 // ---- registered base vectors --------------------------------------------------------------------------
-struct BaseVec {
-    void* bases = nullptr;       // Affine<F>[n] on `cuda_device`
-    uint8_t* inf = nullptr;      // n flags or nullptr
-    size_t n = 0;
-    int cuda_device = 0;
-    bool g2 = false;
-    bool owned = true;
-    void* table = nullptr;       // Affine<F>[nwin(table_c)][n]: 2^(table_c*w) * P_i, or nullptr
-    uint32_t table_c = 0;
-};
-std::mutex g_bases_mu;
-std::unordered_map<uint64_t, BaseVec> g_bases;
-uint64_t g_next_handle = 1;
-
 template <class F>
 int32_t register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle, bool g2) {
     cudaStream_t s;
     MPC_TRY(enter(&s));
     MPC_ARG_CHECK(handle && (n == 0 || bases_xy));
-    BaseVec v;
-    v.n = n;
-    v.g2 = g2;
-    v.cuda_device = current_device_info()->cuda_device;
-    MPC_CUDA_TRY(cudaMalloc(&v.bases, (n ? n : 1) * sizeof(Affine<F>)));
-    MPC_CUDA_TRY(cudaMemcpyAsync(v.bases, bases_xy, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, s));
+    BaseRef v = std::make_shared<BaseVec>();
+    v->n = n;
+    v->g2 = g2;
+    v->dev_index = current_device_index();
+    v->cuda_device = current_device_info()->cuda_device;
+    MPC_CUDA_TRY(cudaMalloc(&v->bases, (n ? n : 1) * sizeof(Affine<F>)));
+    MPC_CUDA_TRY(cudaMemcpyAsync(v->bases, bases_xy, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, s));
     if (inf) {
         bool any = false;
         for (size_t i = 0; i < n && !any; i++) any = inf[i] != 0;
         if (any) {
-            MPC_CUDA_TRY(cudaMalloc((void**)&v.inf, n));
-            MPC_CUDA_TRY(cudaMemcpyAsync(v.inf, inf, n, cudaMemcpyHostToDevice, s));
+            MPC_CUDA_TRY(cudaMalloc((void**)&v->inf, n));
+            MPC_CUDA_TRY(cudaMemcpyAsync(v->inf, inf, n, cudaMemcpyHostToDevice, s));
         }
     }
     MPC_CUDA_TRY(cudaStreamSynchronize(s));
-    std::lock_guard<std::mutex> lk(g_bases_mu);
-    *handle = g_next_handle++;
-    g_bases[*handle] = v;
+    *handle = registry_add(v);
     return MPC_CUDA_OK;
 }
 
-int32_t find_bases(uint64_t handle, bool g2, size_t offset, size_t n, BaseVec* out) {
-    std::lock_guard<std::mutex> lk(g_bases_mu);
-    auto it = g_bases.find(handle);
-    if (it == g_bases.end() || it->second.g2 != g2) {
-        set_error("unknown %s base handle %llu", g2 ? "G2" : "G1", (unsigned long long)handle);
-        return MPC_CUDA_ERR_HANDLE;
+// the vector cut into `parts` point ranges, range k resident on device k mod n_dev of the init list
+template <class F>
+int32_t register_bases_sharded(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint32_t parts, uint64_t* handle,
+                               bool g2) {
+    MPC_TRY(enter(nullptr));
+    MPC_ARG_CHECK(handle && (n == 0 || bases_xy) && parts >= 1 && parts <= 64);
+    const int n_dev = device_list_size();
+    BaseRef parent = std::make_shared<BaseVec>();
+    parent->n = n;
+    parent->g2 = g2;
+    parent->owned = false;
+    for (uint32_t k = 0; k < parts; k++) {
+        size_t lo = n / parts * k + std::min<size_t>(k, n % parts);
+        size_t len = n / parts + (k < n % parts ? 1 : 0);
+        DeviceScope scope((int)(k % n_dev));      // more parts than devices: round robin (single-GPU tests)
+        MPC_TRY(scope.rc);
+        uint64_t h = 0;
+        MPC_TRY(register_bases<F>(bases_xy ? bases_xy + lo * (sizeof(Affine<F>) / 8) : nullptr, inf ? inf + lo : nullptr, len,
+                                  &h, g2));
+        BaseSnap snap;
+        MPC_TRY(registry_find(h, g2, 0, 0, &snap));
+        parent->parts.push_back(snap.ref);
+        parent->lo.push_back(lo);
+        MPC_TRY(mpc_cuda_msm_release_bases(h));      // the parent keeps the only reference
     }
-    if (offset > it->second.n || n > it->second.n - offset) {
-        set_error("base range [%zu, %zu) outside registered vector of %zu points", offset, offset + n, it->second.n);
-        return MPC_CUDA_ERR_ARG;
-    }
-    if (it->second.cuda_device != current_device_info()->cuda_device) {
-        set_error("base handle %llu lives on CUDA device %d, calling thread uses %d", (unsigned long long)handle,
-                  it->second.cuda_device, current_device_info()->cuda_device);
-        return MPC_CUDA_ERR_HANDLE;
-    }
-    *out = it->second;
+    parent->lo.push_back(n);
+    *handle = registry_add(parent);
     return MPC_CUDA_OK;
 }
 
-TableRef table_of(const BaseVec& v, size_t offset) {
+inline TableRef table_of(const BaseSnap& v, size_t offset) {
     TableRef t;
     t.table = v.table;
     t.c = v.table_c;
@@ -818,35 +863,61 @@ TableRef table_of(const BaseVec& v, size_t offset) {
     return t;
 }
 
-// T[w][i] = 2^(c*w) * P_i in affine form, one thread per base (c doublings per window, one inversion per
-// entry; run once per registered CRS)
+// ---- window table T[w][i] = 2^(c*w) * P_i in affine form -------------------------------------------------
+// One thread owns PRE_K consecutive bases.  Pass 1 walks each base's doubling chain in Jacobian coordinates
+// (2M + 5S per doubling), leaving X, Y in the table slot and Z in scratch, and multiplies the Z's into a
+// running prefix product kept in scratch; ONE field inversion per thread (Montgomery's trick,
+// ff/src/fields/mod.rs:597-660 batch_inversion) then normalises all PRE_K * (nwin - 1) entries on the way
+// back.  The cost that remains is the 253 doublings per base.
+constexpr int PRE_K = 4;
+
 template <class F>
 __global__ void __launch_bounds__(ACC_THREADS) k_precompute(const Affine<F>* __restrict__ bases,
                                                             const uint8_t* __restrict__ inf, size_t n, uint32_t c,
-                                                            uint32_t nwin, Affine<F>* __restrict__ table) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Affine<F> pt = load_pod_ro(bases + i);
-    store_pod(table + i, pt);
-    if (inf && inf[i]) return;                 // never referenced: its digits are zero
-    XYZZ<F> acc;
-    acc.x = pt.x; acc.y = pt.y; acc.zz = F::one(); acc.zzz = F::one();
-    for (uint32_t w = 1; w < nwin; w++) {
-        for (uint32_t k = 0; k < c; k++) xyzz_dbl(acc);
-        Affine<F> r;
-        xyzz_to_affine(acc, r.x, r.y);
-        store_pod(table + (size_t)w * n + i, r);
-        acc.x = r.x; acc.y = r.y; acc.zz = F::one(); acc.zzz = F::one();
+                                                            uint32_t nwin, Affine<F>* __restrict__ table,
+                                                            F* __restrict__ zs /* [nwin-1][n] */,
+                                                            F* __restrict__ prefix /* [nwin-1][n] */) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i0 = t * PRE_K;
+    if (i0 >= n) return;
+    size_t i1 = i0 + PRE_K < n ? i0 + PRE_K : n;
+    F run = F::one();
+    for (size_t i = i0; i < i1; i++) {
+        Affine<F> pt = load_pod_ro(bases + i);
+        store_pod(table + i, pt);
+        if (inf && inf[i]) continue;               // never referenced: its digits are zero
+        Jac<F> acc;
+        acc.x = pt.x; acc.y = pt.y; acc.z = F::one();
+        for (uint32_t w = 1; w < nwin; w++) {
+            for (uint32_t k = 0; k < c; k++) jac_dbl(acc);
+            Affine<F> raw;
+            raw.x = acc.x; raw.y = acc.y;
+            size_t slot = (size_t)(w - 1) * n + i;
+            store_pod(table + (size_t)w * n + i, raw);
+            store_pod(zs + slot, acc.z);
+            store_pod(prefix + slot, run);          // product of every Z before this one
+            run = mul(run, acc.z);                  // Z != 0: the points have odd prime order
+        }
+    }
+    F invrun = inv(run);
+    for (size_t i = i1; i-- > i0;) {
+        if (inf && inf[i]) continue;
+        for (uint32_t w = nwin - 1; w >= 1; w--) {
+            size_t slot = (size_t)(w - 1) * n + i;
+            F z = load_pod(zs + slot), pre = load_pod(prefix + slot);
+            F zi = mul(invrun, pre);                // 1 / Z of this entry
+            invrun = mul(invrun, z);
+            F zi2 = sqr(zi);
+            Affine<F> e = load_pod(table + (size_t)w * n + i);
+            e.x = mul(e.x, zi2);
+            e.y = mul(e.y, mul(zi2, zi));
+            store_pod(table + (size_t)w * n + i, e);
+        }
     }
 }
 
 template <class F>
-int32_t precompute(uint64_t handle, uint32_t window_bits, bool g2) {
-    cudaStream_t s;
-    MPC_TRY(enter(&s));
-    MPC_ARG_CHECK(window_bits == 0 || (window_bits >= 3 && window_bits <= MAX_WINDOW_BITS));
-    BaseVec v;
-    MPC_TRY(find_bases(handle, g2, 0, 0, &v));
+int32_t precompute_one(const BaseSnap& v, uint64_t handle, uint32_t window_bits, cudaStream_t s) {
     uint32_t c = window_bits;
     if (c == 0) {
         uint32_t l = log2_ceil(v.n ? v.n : 1);
@@ -858,27 +929,45 @@ int32_t precompute(uint64_t handle, uint32_t window_bits, bool g2) {
     void* table = nullptr;
     MPC_CUDA_TRY(cudaMalloc(&table, (size_t)nwin * (v.n ? v.n : 1) * sizeof(Affine<F>)));
     if (v.n) {
-        k_precompute<F><<<(unsigned)((v.n + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, s>>>(
-            (const Affine<F>*)v.bases, v.inf, v.n, c, nwin, (Affine<F>*)table);
+        Scratch sz, sp;
+        F *zs, *prefix;
+        ProfileScope prof("msm_precompute", s);
+        if (sz.alloc(&zs, (size_t)(nwin - 1) * v.n, s) != MPC_CUDA_OK || sp.alloc(&prefix, (size_t)(nwin - 1) * v.n, s) != MPC_CUDA_OK) {
+            cudaFree(table);
+            return MPC_CUDA_ERR_CUDA;
+        }
+        size_t threads = (v.n + PRE_K - 1) / PRE_K;
+        k_precompute<F><<<(unsigned)((threads + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, s>>>(
+            (const Affine<F>*)v.bases, v.inf, v.n, c, nwin, (Affine<F>*)table, zs, prefix);
         MPC_KERNEL_CHECK();
     }
     MPC_CUDA_TRY(cudaStreamSynchronize(s));
-    void* old = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g_bases_mu);
-        auto it = g_bases.find(handle);
-        if (it == g_bases.end()) {
-            cudaFree(table);
-            set_error("base handle %llu released during precomputation", (unsigned long long)handle);
-            return MPC_CUDA_ERR_HANDLE;
-        }
-        old = it->second.table;
-        it->second.table = table;
-        it->second.table_c = c;
+    if (handle) {
+        int32_t rc = registry_set_table(handle, table, c);
+        if (rc != MPC_CUDA_OK) cudaFree(table);
+        return rc;
     }
-    if (old) {
-        MPC_CUDA_TRY(cudaDeviceSynchronize());
-        cudaFree(old);
+    // a part of a sharded vector: reachable only through its parent, which the caller holds
+    BaseVec& bv = *v.ref;
+    if (bv.table) bv.retired.push_back(bv.table);
+    bv.table = table;
+    bv.table_c = c;
+    return MPC_CUDA_OK;
+}
+
+template <class F>
+int32_t precompute(uint64_t handle, uint32_t window_bits, bool g2) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_ARG_CHECK(window_bits == 0 || (window_bits >= 3 && window_bits <= MAX_WINDOW_BITS));
+    BaseSnap v;
+    MPC_TRY(registry_find(handle, g2, 0, 0, &v));
+    if (v.ref->parts.empty()) return precompute_one<F>(v, handle, window_bits, s);
+    // every part picks its window width for its own length unless the caller fixed one
+    for (size_t k = 0; k < v.ref->parts.size(); k++) {
+        DeviceScope scope(v.ref->parts[k]->dev_index);
+        MPC_TRY(scope.rc);
+        MPC_TRY(precompute_one<F>(snapshot_of(v.ref->parts[k]), 0, window_bits, scope.s));
     }
     return MPC_CUDA_OK;
 }
@@ -906,183 +995,174 @@ int32_t msm_emit(const Affine<F>* bases, const uint8_t* inf, const Fr* scalars_d
     return MPC_CUDA_OK;
 }
 
+// Host-buffer MSM (AffineMsm::msm as the Rust shim calls it): the scalars and the bases cross PCIe inside
+// the call.  Large inputs are streamed as point-range chunks on a second stream so the copy of chunk j+1
+// overlaps the sort and bucket accumulation of chunk j; all chunks add into one bucket set.
+struct CopyLane {
+    static constexpr int MAX_CHUNKS = 16;
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[MAX_CHUNKS + 1] = {};
+    ~CopyLane() {
+        if (s) cudaStreamSynchronize(s);             // error paths: no copy may outlive the buffers it writes
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+        if (s) cudaStreamDestroy(s);
+    }
+};
+
+inline uint32_t host_chunks_for(size_t n) {
+    int64_t k = g_opt_msm_host_chunks.load(std::memory_order_relaxed);
+    if (k <= 0) k = n >= ((size_t)1 << 23) ? 8 : n >= ((size_t)1 << 21) ? 4 : n >= ((size_t)1 << 19) ? 2 : 1;
+    if (k > 16) k = 16;
+    if ((size_t)k > n) k = (int64_t)(n ? n : 1);
+    return (uint32_t)k;
+}
+
 template <class F>
 int32_t msm_host(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars, size_t n, uint64_t* out_xy,
                  uint8_t* out_inf) {
+    constexpr int N = sizeof(F) / 4;
     cudaStream_t s;
     MPC_TRY(enter(&s));
     MPC_ARG_CHECK(out_xy && out_inf && (n == 0 || (bases_xy && scalars)));
-    Scratch sb, si, ss;
+    Scratch sb, si, ss, s_res, s_out;
     Affine<F>* db;
     uint8_t* di = nullptr;
     Fr* dsc;
+    XYZZ<F>* res;
+    uint32_t* out;
     MPC_TRY(sb.alloc(&db, n, s));
     MPC_TRY(ss.alloc(&dsc, n, s));
-    MPC_CUDA_TRY(cudaMemcpyAsync(db, bases_xy, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, s));
-    MPC_CUDA_TRY(cudaMemcpyAsync(dsc, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
-    if (inf && n) {
-        MPC_TRY(si.alloc(&di, n, s));
-        MPC_CUDA_TRY(cudaMemcpyAsync(di, inf, n, cudaMemcpyHostToDevice, s));
+    if (inf && n) MPC_TRY(si.alloc(&di, n, s));
+    MPC_TRY(s_res.alloc(&res, 1, s));
+    MPC_TRY(s_out.alloc(&out, 3 * N + 4, s));
+    CopyLane lane;                                   // destroyed after the final synchronisation below
+    if (n == 0) {
+        MPC_CUDA_TRY(cudaMemsetAsync(res, 0, sizeof(XYZZ<F>), s));
+    } else {
+        const uint32_t K = host_chunks_for(n);
+        const size_t cap = (n + K - 1) / K;
+        MPC_CUDA_TRY(cudaStreamCreateWithFlags(&lane.s, cudaStreamNonBlocking));
+        // the buffers were allocated stream-ordered on s: the copy stream may touch them only after that point
+        MPC_CUDA_TRY(cudaEventCreateWithFlags(&lane.ev[CopyLane::MAX_CHUNKS], cudaEventDisableTiming));
+        MPC_CUDA_TRY(cudaEventRecord(lane.ev[CopyLane::MAX_CHUNKS], s));
+        MPC_CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.ev[CopyLane::MAX_CHUNKS], 0));
+        ProfileScope prof_total("msm_total", s);
+        MsmJob<F> job;
+        MPC_TRY(job.begin(n, cap, s, nullptr));
+        for (uint32_t k = 0; k < K; k++) {
+            size_t lo = (size_t)k * cap, len = lo + cap <= n ? cap : (lo < n ? n - lo : 0);
+            if (!len) break;
+            MPC_CUDA_TRY(cudaMemcpyAsync(dsc + lo, scalars + lo * 4, len * sizeof(Fr), cudaMemcpyHostToDevice, lane.s));
+            if (di) MPC_CUDA_TRY(cudaMemcpyAsync(di + lo, inf + lo, len, cudaMemcpyHostToDevice, lane.s));
+            MPC_CUDA_TRY(cudaMemcpyAsync(db + lo, bases_xy + lo * (sizeof(Affine<F>) / 8), len * sizeof(Affine<F>),
+                                         cudaMemcpyHostToDevice, lane.s));
+            MPC_CUDA_TRY(cudaEventCreateWithFlags(&lane.ev[k], cudaEventDisableTiming));
+            MPC_CUDA_TRY(cudaEventRecord(lane.ev[k], lane.s));
+        }
+        for (uint32_t k = 0; k < K; k++) {
+            size_t lo = (size_t)k * cap, len = lo + cap <= n ? cap : (lo < n ? n - lo : 0);
+            if (!len) break;
+            MPC_CUDA_TRY(cudaStreamWaitEvent(s, lane.ev[k], 0));
+            MPC_TRY(job.chunk(db + lo, di ? di + lo : nullptr, dsc + lo, len));
+        }
+        MPC_TRY(job.finish(res));
     }
-    return msm_emit<F>(db, di, dsc, n, 0, nullptr, out_xy, out_inf, s);
-}
-
-template <class F>
-int32_t msm_handle_host(uint64_t handle, size_t offset, const uint64_t* scalars, size_t n, uint64_t* out_xy,
-                        uint8_t* out_inf, bool g2) {
-    cudaStream_t s;
-    MPC_TRY(enter(&s));
-    MPC_ARG_CHECK(out_xy && out_inf && (n == 0 || scalars));
-    BaseVec v;
-    MPC_TRY(find_bases(handle, g2, offset, n, &v));
-    Scratch ss;
-    Fr* dsc;
-    MPC_TRY(ss.alloc(&dsc, n, s));
-    MPC_CUDA_TRY(cudaMemcpyAsync(dsc, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
-    TableRef tbl = table_of(v, offset);
-    return msm_emit<F>((const Affine<F>*)v.bases + offset, v.inf ? v.inf + offset : nullptr, dsc, n, 0, nullptr, out_xy,
-                       out_inf, s, &tbl);
-}
-
-template <class F>
-int32_t generate(const uint32_t* gx, const uint32_t* gy, uint64_t seed, size_t first, size_t n, uint64_t* out,
-                 void* stream) {
-    cudaStream_t s;
-    MPC_TRY(enter(&s));
-    if (n == 0) return MPC_CUDA_OK;
-    MPC_ARG_CHECK(out);
-    Affine<F> g;
-    memcpy(&g.x, gx, sizeof(F));
-    memcpy(&g.y, gy, sizeof(F));
-    k_generate<F><<<(unsigned)((n + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, pick_stream(stream, s)>>>(
-        g, seed, first, n, (Affine<F>*)out);
+    k_emit<F><<<1, 32, 0, s>>>(res, 1, 0, out);
     MPC_KERNEL_CHECK();
+    uint32_t host[2 * N + 1];
+    MPC_CUDA_TRY(cudaMemcpyAsync(host, out, sizeof(host), cudaMemcpyDeviceToHost, s));
+    MPC_CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(out_xy, host, 2 * N * sizeof(uint32_t));
+    *out_inf = (uint8_t)host[2 * N];
+    return MPC_CUDA_OK;
+}
+
+struct EventHolder {
+    cudaEvent_t e = nullptr;
+    EventHolder() {}
+    EventHolder(const EventHolder&) = delete;
+    EventHolder& operator=(const EventHolder&) = delete;
+    ~EventHolder() { if (e) cudaEventDestroy(e); }
+    int32_t create() { MPC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return MPC_CUDA_OK; }
+};
+
+// one part of a sharded MSM, on the calling thread's CURRENT device (the caller holds a DeviceScope):
+// scalars [lo, hi) of the part -> Jacobian partial -> peer copy into slot `dst` on the home device
+template <class F>
+int32_t msm_shard_part(const BaseSnap& part, size_t first, size_t len, const uint64_t* scalars_host, const Fr* scalars_dev,
+                       uint32_t* dst, int home_cuda, cudaEvent_t home_ready, cudaEvent_t done, cudaStream_t s) {
+    constexpr int N = sizeof(F) / 4;
+    Scratch ssc, sjac;
+    Fr* dsc = nullptr;
+    uint32_t* jac;
+    MPC_TRY(sjac.alloc(&jac, 3 * N, s));
+    const Fr* sc = scalars_dev;
+    if (!sc) {
+        MPC_TRY(ssc.alloc(&dsc, len, s));
+        MPC_CUDA_TRY(cudaMemcpyAsync(dsc, scalars_host, len * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        sc = dsc;
+    }
+    TableRef tbl = table_of(part, first);
+    MPC_TRY(msm_emit<F>((const Affine<F>*)part.bases + first, part.inf ? part.inf + first : nullptr, sc, len, 1, jac, nullptr,
+                        nullptr, s, &tbl));
+    MPC_CUDA_TRY(cudaStreamWaitEvent(s, home_ready, 0));
+    MPC_CUDA_TRY(cudaMemcpyPeerAsync(dst, home_cuda, jac, part.ref->cuda_device, 3 * N * sizeof(uint32_t), s));
+    MPC_CUDA_TRY(cudaEventRecord(done, s));
+    return MPC_CUDA_OK;
+}
+
+// Σ over the parts of a sharded vector: part k runs the whole pipeline on device k and leaves a Jacobian
+// partial; the partials travel to the calling thread's device over NVLink (peer copies) where they are added
+// and normalised (no collective exists for elliptic-curve addition: gather + add).
+// scalars: host pointer (scalars_dev == nullptr), or one device pointer per part holding that part's slice
+// of [offset, offset + n).
+template <class F>
+int32_t msm_sharded(const BaseSnap& v, size_t offset, const uint64_t* scalars_host, const uint64_t* const* scalars_dev,
+                    size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+    constexpr int N = sizeof(F) / 4;
+    cudaStream_t s0;
+    MPC_TRY(enter(&s0));
+    MPC_TRY(enable_peer_access());
+    const BaseVec& parent = *v.ref;
+    const size_t P = parent.parts.size();
+    const int home_cuda = current_device_info()->cuda_device;
+    Scratch s_gather, s_pts, s_out;
+    uint32_t *gather, *out;
+    XYZZ<F>* pts;
+    MPC_TRY(s_gather.alloc(&gather, P * 3 * N, s0));
+    MPC_TRY(s_pts.alloc(&pts, P, s0));
+    MPC_TRY(s_out.alloc(&out, 3 * N + 4, s0));
+    MPC_CUDA_TRY(cudaMemsetAsync(gather, 0, P * 3 * N * sizeof(uint32_t), s0));       // z = 0: infinity
+    EventHolder home_ready;
+    MPC_TRY(home_ready.create());
+    MPC_CUDA_TRY(cudaEventRecord(home_ready.e, s0));
+    std::vector<EventHolder> done(P);
+    for (size_t k = 0; k < P; k++) {
+        size_t plo = parent.lo[k], phi = parent.lo[k + 1];
+        size_t lo = std::max(plo, offset), hi = std::min(phi, offset + n);      // this part's share of the range
+        if (lo >= hi) continue;
+        BaseSnap part = snapshot_of(parent.parts[k]);
+        MPC_TRY(done[k].create());
+        DeviceScope scope(part.ref->dev_index);
+        MPC_TRY(scope.rc);
+        MPC_TRY(msm_shard_part<F>(part, lo - plo, hi - lo, scalars_host ? scalars_host + (lo - offset) * 4 : nullptr,
+                                  scalars_dev ? (const Fr*)scalars_dev[k] : nullptr, gather + k * 3 * N, home_cuda,
+                                  home_ready.e, done[k].e, scope.s));
+    }
+    for (size_t k = 0; k < P; k++)
+        if (done[k].e) MPC_CUDA_TRY(cudaStreamWaitEvent(s0, done[k].e, 0));
+    k_jac_to_xyzz<F><<<(unsigned)((P + 127) / 128), 128, 0, s0>>>((const Jac<F>*)gather, (uint32_t)P, pts);
+    MPC_KERNEL_CHECK();
+    k_emit<F><<<1, 32, 0, s0>>>(pts, (uint32_t)P, 0, out);
+    MPC_KERNEL_CHECK();
+    uint32_t host[2 * N + 1];
+    MPC_CUDA_TRY(cudaMemcpyAsync(host, out, sizeof(host), cudaMemcpyDeviceToHost, s0));
+    MPC_CUDA_TRY(cudaStreamSynchronize(s0));
+    // the parts' scratch was freed stream-ordered on their own streams; nothing else to wait for
+    memcpy(out_xy, host, 2 * N * sizeof(uint32_t));
+    *out_inf = (uint8_t)host[2 * N];
     return MPC_CUDA_OK;
 }
 
 }  // namespace
-
-extern "C" {
-
-int32_t mpc_cuda_msm_g1(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars_mont, size_t n,
-                        uint64_t out_xy[12], uint8_t* out_inf) {
-    return msm_host<Fq>(bases_xy, inf, scalars_mont, n, out_xy, out_inf);
-}
-
-int32_t mpc_cuda_msm_g2(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars_mont, size_t n,
-                        uint64_t out_xy[24], uint8_t* out_inf) {
-    return msm_host<Fq2>(bases_xy, inf, scalars_mont, n, out_xy, out_inf);
-}
-
-int32_t mpc_cuda_msm_g1_register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle) {
-    return register_bases<Fq>(bases_xy, inf, n, handle, false);
-}
-
-int32_t mpc_cuda_msm_g2_register_bases(const uint64_t* bases_xy, const uint8_t* inf, size_t n, uint64_t* handle) {
-    return register_bases<Fq2>(bases_xy, inf, n, handle, true);
-}
-
-int32_t mpc_cuda_msm_g1_register_bases_dev(const uint64_t* bases_xy_dev, size_t n, uint64_t* handle) {
-    MPC_TRY(enter(nullptr));
-    MPC_ARG_CHECK(handle && (n == 0 || bases_xy_dev));
-    BaseVec v;
-    v.bases = (void*)bases_xy_dev;
-    v.n = n;
-    v.cuda_device = current_device_info()->cuda_device;
-    v.owned = false;
-    std::lock_guard<std::mutex> lk(g_bases_mu);
-    *handle = g_next_handle++;
-    g_bases[*handle] = v;
-    return MPC_CUDA_OK;
-}
-
-int32_t mpc_cuda_msm_release_bases(uint64_t handle) {
-    MPC_TRY(enter(nullptr));
-    BaseVec v;
-    {
-        std::lock_guard<std::mutex> lk(g_bases_mu);
-        auto it = g_bases.find(handle);
-        if (it == g_bases.end()) {
-            set_error("unknown base handle %llu", (unsigned long long)handle);
-            return MPC_CUDA_ERR_HANDLE;
-        }
-        v = it->second;
-        g_bases.erase(it);
-    }
-    int cur = 0;
-    MPC_CUDA_TRY(cudaGetDevice(&cur));
-    MPC_CUDA_TRY(cudaSetDevice(v.cuda_device));
-    if (v.owned) {
-        cudaFree(v.bases);
-        if (v.inf) cudaFree(v.inf);
-    }
-    if (v.table) cudaFree(v.table);
-    MPC_CUDA_TRY(cudaSetDevice(cur));
-    return MPC_CUDA_OK;
-}
-
-int32_t mpc_cuda_msm_g1_precompute(uint64_t handle, uint32_t window_bits) {
-    return precompute<Fq>(handle, window_bits, false);
-}
-
-int32_t mpc_cuda_msm_g2_precompute(uint64_t handle, uint32_t window_bits) {
-    return precompute<Fq2>(handle, window_bits, true);
-}
-
-int32_t mpc_cuda_msm_g1_handle(uint64_t handle, size_t offset, const uint64_t* scalars_mont, size_t n,
-                               uint64_t out_xy[12], uint8_t* out_inf) {
-    return msm_handle_host<Fq>(handle, offset, scalars_mont, n, out_xy, out_inf, false);
-}
-
-int32_t mpc_cuda_msm_g2_handle(uint64_t handle, size_t offset, const uint64_t* scalars_mont, size_t n,
-                               uint64_t out_xy[24], uint8_t* out_inf) {
-    return msm_handle_host<Fq2>(handle, offset, scalars_mont, n, out_xy, out_inf, true);
-}
-
-int32_t mpc_cuda_msm_g1_handle_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
-                                   uint64_t* out_jac_dev, void* stream) {
-    cudaStream_t s;
-    MPC_TRY(enter(&s));
-    MPC_ARG_CHECK(out_jac_dev && (n == 0 || scalars_mont_dev));
-    BaseVec v;
-    MPC_TRY(find_bases(handle, false, offset, n, &v));
-    TableRef tbl = table_of(v, offset);
-    return msm_emit<Fq>((const Affine<Fq>*)v.bases + offset, v.inf ? v.inf + offset : nullptr,
-                        (const Fr*)scalars_mont_dev, n, 1, (uint32_t*)out_jac_dev, nullptr, nullptr,
-                        pick_stream(stream, s), &tbl);
-}
-
-int32_t mpc_cuda_g1_sum_partials_dev(const uint64_t* jac_dev, uint32_t count, uint64_t out_xy[12], uint8_t* out_inf,
-                                     void* stream) {
-    cudaStream_t s0;
-    MPC_TRY(enter(&s0));
-    cudaStream_t s = pick_stream(stream, s0);
-    MPC_ARG_CHECK(out_xy && out_inf && (count == 0 || jac_dev));
-    Scratch sx, so;
-    XYZZ<Fq>* pts;
-    uint32_t* out;
-    MPC_TRY(sx.alloc(&pts, count, s));
-    MPC_TRY(so.alloc(&out, 40, s));
-    if (count) {
-        k_jac_to_xyzz<Fq><<<(count + 127) / 128, 128, 0, s>>>((const Jac<Fq>*)jac_dev, count, pts);
-        MPC_KERNEL_CHECK();
-    }
-    k_emit<Fq><<<1, 32, 0, s>>>(pts, count, 0, out);
-    MPC_KERNEL_CHECK();
-    uint32_t host[25];
-    MPC_CUDA_TRY(cudaMemcpyAsync(host, out, sizeof(host), cudaMemcpyDeviceToHost, s));
-    MPC_CUDA_TRY(cudaStreamSynchronize(s));
-    memcpy(out_xy, host, 24 * sizeof(uint32_t));
-    *out_inf = (uint8_t)host[24];
-    return MPC_CUDA_OK;
-}
-
-int32_t mpc_cuda_g1_generate_dev(uint64_t seed, size_t first, size_t n, uint64_t* out_xy_dev, void* stream) {
-    return generate<Fq>(consts::G1_GEN_X, consts::G1_GEN_Y, seed, first, n, out_xy_dev, stream);
-}
-
-int32_t mpc_cuda_g2_generate_dev(uint64_t seed, size_t first, size_t n, uint64_t* out_xy_dev, void* stream) {
-    return generate<Fq2>(consts::G2_GEN_X, consts::G2_GEN_Y, seed, first, n, out_xy_dev, stream);
-}
-
-}  // extern "C"

@@ -231,8 +231,11 @@ Fr fr_from_limbs(const uint32_t* l) {
     return r;
 }
 
-// make sure the tables a transform of size 2^log_n needs exist on the current device
-int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s, DomainCache** out) {
+// Make sure the tables a transform of size 2^log_n needs exist on the current device and return a COPY of the
+// cache entry taken under the lock.  Published tables are never freed: when a larger coset table replaces a
+// smaller one, the old arrays stay allocated (retired) because another party thread may already hold their
+// pointers for a launch it has not issued yet (LocalTestNet runs all parties on one device).
+int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s, DomainCache* out) {
     std::lock_guard<std::mutex> lk(g_ntt_mu);
     DomainCache& d = g_cache[dev_index];
     bool dirty = false;
@@ -253,43 +256,46 @@ int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s,
     for (uint32_t l = 2; l <= log_n; l++) {
         if (d.tw[l]) continue;
         size_t count = (size_t)1 << (l - 1);
-        MPC_CUDA_TRY(cudaMalloc((void**)&d.tw[l], count * sizeof(Fr)));
-        k_powers<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d.consts + l, 0, count, d.tw[l]);
+        Fr* t = nullptr;
+        MPC_CUDA_TRY(cudaMalloc((void**)&t, count * sizeof(Fr)));
+        k_powers<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d.consts + l, 0, count, t);
         MPC_KERNEL_CHECK();
-        dirty = true;
+        MPC_CUDA_TRY(cudaStreamSynchronize(s));       // publish only complete tables
+        d.tw[l] = t;
     }
     if (coset) {
         const size_t lo_n = (size_t)1 << COSET_LO_BITS;
         if (!d.g_lo) {
-            MPC_CUDA_TRY(cudaMalloc((void**)&d.g_lo, lo_n * sizeof(Fr)));
-            MPC_CUDA_TRY(cudaMalloc((void**)&d.gi_lo, lo_n * sizeof(Fr)));
-            k_powers<<<(unsigned)(lo_n / 256), 256, 0, s>>>(d.gen_pair, 0, lo_n, d.g_lo);
+            Fr *a = nullptr, *b = nullptr;
+            MPC_CUDA_TRY(cudaMalloc((void**)&a, lo_n * sizeof(Fr)));
+            MPC_CUDA_TRY(cudaMalloc((void**)&b, lo_n * sizeof(Fr)));
+            k_powers<<<(unsigned)(lo_n / 256), 256, 0, s>>>(d.gen_pair, 0, lo_n, a);
             MPC_KERNEL_CHECK();
-            k_powers<<<(unsigned)(lo_n / 256), 256, 0, s>>>(d.gen_pair + 1, 0, lo_n, d.gi_lo);
+            k_powers<<<(unsigned)(lo_n / 256), 256, 0, s>>>(d.gen_pair + 1, 0, lo_n, b);
             MPC_KERNEL_CHECK();
-            dirty = true;
+            MPC_CUDA_TRY(cudaStreamSynchronize(s));
+            d.g_lo = a;
+            d.gi_lo = b;
         }
         uint32_t need = log_n > COSET_LO_BITS ? log_n - COSET_LO_BITS : 0;
         if (need && (!d.g_hi || need > d.hi_bits)) {
-            if (d.g_hi) {
-                MPC_CUDA_TRY(cudaDeviceSynchronize());      // other streams may still read the old tables
-                cudaFree(d.g_hi);
-                cudaFree(d.gi_hi);
-            }
             size_t hi_n = (size_t)1 << need;
-            MPC_CUDA_TRY(cudaMalloc((void**)&d.g_hi, hi_n * sizeof(Fr)));
-            MPC_CUDA_TRY(cudaMalloc((void**)&d.gi_hi, hi_n * sizeof(Fr)));
-            k_powers<<<(unsigned)((hi_n + 255) / 256), 256, 0, s>>>(d.gen_pair, COSET_LO_BITS, hi_n, d.g_hi);
+            Fr *a = nullptr, *b = nullptr;
+            MPC_CUDA_TRY(cudaMalloc((void**)&a, hi_n * sizeof(Fr)));
+            MPC_CUDA_TRY(cudaMalloc((void**)&b, hi_n * sizeof(Fr)));
+            k_powers<<<(unsigned)((hi_n + 255) / 256), 256, 0, s>>>(d.gen_pair, COSET_LO_BITS, hi_n, a);
             MPC_KERNEL_CHECK();
-            k_powers<<<(unsigned)((hi_n + 255) / 256), 256, 0, s>>>(d.gen_pair + 1, COSET_LO_BITS, hi_n, d.gi_hi);
+            k_powers<<<(unsigned)((hi_n + 255) / 256), 256, 0, s>>>(d.gen_pair + 1, COSET_LO_BITS, hi_n, b);
             MPC_KERNEL_CHECK();
+            MPC_CUDA_TRY(cudaStreamSynchronize(s));
+            // the superseded (smaller) tables stay allocated: total retired size < the live tables
+            d.g_hi = a;
+            d.gi_hi = b;
             d.hi_bits = need;
-            dirty = true;
         }
     }
-    // tables are shared by every stream of the device: publish them only once they are complete
-    if (dirty) MPC_CUDA_TRY(cudaStreamSynchronize(s));
-    *out = &d;
+    (void)dirty;
+    *out = d;
     return MPC_CUDA_OK;
 }
 
@@ -301,8 +307,9 @@ int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStr
     if (log_n == 0) return MPC_CUDA_OK;      // size-1 domain: every kind is the identity (size_inv = 1, g^0 = 1)
     const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
     const bool coset = kind >= MPC_CUDA_NTT_COSET_FFT;
-    DomainCache* d;
-    MPC_TRY(ensure_tables(current_device_index(), log_n, coset, s, &d));
+    DomainCache dc;
+    MPC_TRY(ensure_tables(current_device_index(), log_n, coset, s, &dc));
+    const DomainCache* d = &dc;
 
     ProfileScope prof("ntt", s);
     const size_t n = (size_t)1 << log_n;
@@ -352,20 +359,24 @@ int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStr
 // ---- multi-GPU: the stages that cross device boundaries -------------------------------------------------
 // With the vector block-distributed over g = 2^k devices (device q holds indices [q n/g, (q+1) n/g)), the
 // first k DIF stages pair elements n/2, n/4, ..., n/g apart, i.e. equal local offsets on different devices;
-// afterwards every block is an independent size-n/g transform (local k_ntt_pass).  After an all-to-all the
-// calling device holds, for its slice of local offsets l in [l0, l0 + len), the g values D[q][l]; one thread
-// runs the k cross stages for one offset in registers.  kind fft/coset_fft: (22^j scaling,) DIF stages
-// 0..k-1.  kind ifft/coset_ifft: the exact inverse (stages k-1..0 of t = hi w^-1, lo' = lo + t, hi' = lo - t,
-// then g^-1 and, for the coset, 22^-i).  Output layout of the forward transform: device r, local m holds
-// X[m g + bitrev_k(r)] (the usual transposed order of a four-step NTT); the inverse consumes that layout.
+// afterwards every block is an independent size-n/g transform (local k_ntt_pass).  One thread runs the k
+// cross stages for one local offset l in registers, reading the g values D[q][l] through per-block base
+// pointers.  Those pointers are either g planes of a gathered buffer (mpc_cuda_ntt_cross_stage_dev: the
+// caller did the all-to-all, e.g. NCCL across processes) or the blocks themselves on their home devices
+// (mpc_cuda_ntt_fr_sharded_dev: one process, NVLink peer loads and stores inside the kernel — the exchange is
+// fused into the butterflies and no separate transpose pass exists).
+// kind fft/coset_fft: (22^j scaling,) DIF stages 0..k-1.  kind ifft/coset_ifft: the exact inverse (stages
+// k-1..0 of t = hi w^-1, lo' = lo + t, hi' = lo - t, then g^-1 and, for the coset, 22^-i).  Output layout of the
+// forward transform: device r, local m holds X[m g + bitrev_k(r)] (the usual transposed order of a four-step
+// NTT); the inverse consumes that layout.
 constexpr int MAX_LOG_G = 3;
 
 struct CrossArgs {
-    Fr* data;                      // [g][len]
+    Fr* blk[1 << MAX_LOG_G];       // element (q, l) lives at blk[q][l - base]
     const Fr* tw[MAX_LOG_G];       // tw[s] = forward table of domain log_n - s
     const Fr *g_lo, *g_hi;         // 22^(+-i) two-level tables (coset kinds), or nullptr
     const Fr* scale;               // g^-1 (inverse kinds)
-    size_t l0, len;
+    size_t l0, len, base;          // local offsets [l0, l0 + len); blk pointers are biased by `base`
     uint32_t log_n, log_g, inverse;
 };
 
@@ -378,8 +389,9 @@ __global__ void __launch_bounds__(128) k_ntt_cross(CrossArgs a) {
     const bool inverse = a.inverse != 0;
     Fr x[G];
 #pragma unroll
+    for (int q = 0; q < G; q++) x[q] = load_fe(a.blk[q] + (l - a.base));      // all (peer) loads in flight first
+#pragma unroll
     for (int q = 0; q < G; q++) {
-        x[q] = load_fe(a.data + (size_t)q * a.len + t);
         if (!inverse && a.g_lo) {
             size_t j = (size_t)q * blk + l;
             x[q] = mul(x[q], load_fe_ro(a.g_lo + (j & ((1u << COSET_LO_BITS) - 1))));
@@ -426,26 +438,30 @@ __global__ void __launch_bounds__(128) k_ntt_cross(CrossArgs a) {
                 if (a.log_n > COSET_LO_BITS) x[q] = mul(x[q], load_fe_ro(a.g_hi + (i >> COSET_LO_BITS)));
             }
         }
-        store_fe(a.data + (size_t)q * a.len + t, x[q]);
+        store_fe(a.blk[q] + (l - a.base), x[q]);
     }
 }
 
-int32_t ntt_cross_dev(Fr* data, uint32_t log_n, uint32_t log_g, size_t l0, size_t len, uint32_t kind, cudaStream_t s) {
+// blk[q]: where element (q, l0) of the call lives; `base` = the local offset blk[q][0] corresponds to
+int32_t ntt_cross_launch(Fr* const* blk, size_t base, uint32_t log_n, uint32_t log_g, size_t l0, size_t len, uint32_t kind,
+                         cudaStream_t s) {
     MPC_ARG_CHECK(kind <= MPC_CUDA_NTT_COSET_IFFT && log_g >= 1 && log_g <= (uint32_t)MAX_LOG_G);
     MPC_ARG_CHECK(log_n <= MAX_LOG_N && log_n > log_g && l0 + len <= ((size_t)1 << (log_n - log_g)));
     if (len == 0) return MPC_CUDA_OK;
-    MPC_ARG_CHECK(data != nullptr);
     const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
     const bool coset = kind >= MPC_CUDA_NTT_COSET_FFT;
-    DomainCache* d;
-    MPC_TRY(ensure_tables(current_device_index(), log_n, coset, s, &d));
+    DomainCache dc;
+    MPC_TRY(ensure_tables(current_device_index(), log_n, coset, s, &dc));
     CrossArgs a;
     memset(&a, 0, sizeof(a));
-    a.data = data;
-    for (uint32_t st = 0; st < log_g; st++) a.tw[st] = d->tw[log_n - st];
-    if (coset) { a.g_lo = inverse ? d->gi_lo : d->g_lo; a.g_hi = inverse ? d->gi_hi : d->g_hi; }
-    a.scale = d->consts + 48 + log_g;
-    a.l0 = l0; a.len = len; a.log_n = log_n; a.log_g = log_g; a.inverse = inverse;
+    for (uint32_t q = 0; q < (1u << log_g); q++) {
+        MPC_ARG_CHECK(blk[q] != nullptr);
+        a.blk[q] = blk[q];
+    }
+    for (uint32_t st = 0; st < log_g; st++) a.tw[st] = dc.tw[log_n - st];
+    if (coset) { a.g_lo = inverse ? dc.gi_lo : dc.g_lo; a.g_hi = inverse ? dc.gi_hi : dc.g_hi; }
+    a.scale = dc.consts + 48 + log_g;
+    a.l0 = l0; a.len = len; a.base = base; a.log_n = log_n; a.log_g = log_g; a.inverse = inverse;
     unsigned blocks = (unsigned)((len + 127) / 128);
     switch (log_g) {
         case 1: k_ntt_cross<1><<<blocks, 128, 0, s>>>(a); break;
@@ -454,6 +470,150 @@ int32_t ntt_cross_dev(Fr* data, uint32_t log_n, uint32_t log_g, size_t l0, size_
     }
     MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
+}
+
+int32_t ntt_cross_dev(Fr* data, uint32_t log_n, uint32_t log_g, size_t l0, size_t len, uint32_t kind, cudaStream_t s) {
+    MPC_ARG_CHECK(log_g >= 1 && log_g <= (uint32_t)MAX_LOG_G);
+    if (len == 0) return MPC_CUDA_OK;
+    MPC_ARG_CHECK(data != nullptr);
+    Fr* blk[1 << MAX_LOG_G];
+    for (uint32_t q = 0; q < (1u << log_g); q++) blk[q] = data + (size_t)q * len;
+    return ntt_cross_launch(blk, l0, log_n, log_g, l0, len, kind, s);
+}
+
+// ---- one process, g devices: the whole sharded transform -------------------------------------------------
+struct Ev {
+    cudaEvent_t e = nullptr;
+    Ev() {}
+    Ev(const Ev&) = delete;
+    Ev& operator=(const Ev&) = delete;
+    ~Ev() { if (e) cudaEventDestroy(e); }
+};
+
+// every stream waits until all streams reached this point
+int32_t cross_barrier(const int* dev, cudaStream_t* st, Ev* evs, int g) {
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(dev[q]);
+        MPC_TRY(scope.rc);
+        if (!evs[q].e) MPC_CUDA_TRY(cudaEventCreateWithFlags(&evs[q].e, cudaEventDisableTiming));
+        MPC_CUDA_TRY(cudaEventRecord(evs[q].e, st[q]));
+    }
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(dev[q]);
+        MPC_TRY(scope.rc);
+        for (int r = 0; r < g; r++)
+            if (r != q && st[r] != st[q]) MPC_CUDA_TRY(cudaStreamWaitEvent(st[q], evs[r].e, 0));
+    }
+    return MPC_CUDA_OK;
+}
+
+int32_t ntt_sharded_dev(Fr* const* blocks, const int32_t* dev_index, uint32_t log_n, uint32_t log_g, uint32_t kind) {
+    MPC_ARG_CHECK(blocks && kind <= MPC_CUDA_NTT_COSET_IFFT && log_g <= (uint32_t)MAX_LOG_G && log_n <= MAX_LOG_N);
+    const int g = 1 << log_g;
+    if (log_g == 0) {
+        DeviceScope scope(dev_index ? dev_index[0] : current_device_index());
+        MPC_TRY(scope.rc);
+        return ntt_dev(blocks[0], log_n, kind, 1, scope.s);
+    }
+    // every device runs log_g cross stages on a slice of m / g local offsets, so the block must hold >= g elements
+    MPC_ARG_CHECK(log_n >= 2 * log_g);
+    const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
+    int dev[1 << MAX_LOG_G];
+    cudaStream_t st[1 << MAX_LOG_G];
+    bool distinct = false;
+    for (int q = 0; q < g; q++) {
+        dev[q] = dev_index ? dev_index[q] : q;
+        MPC_ARG_CHECK(dev[q] >= 0 && dev[q] < device_list_size() && blocks[q]);
+        if (dev[q] != dev[0]) distinct = true;
+    }
+    if (distinct) MPC_TRY(enable_peer_access());
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(dev[q]);
+        MPC_TRY(scope.rc);
+        st[q] = scope.s;
+    }
+    const size_t m = (size_t)1 << (log_n - log_g), slice = m >> log_g;
+    Ev ev_a[1 << MAX_LOG_G], ev_b[1 << MAX_LOG_G], ev_c[1 << MAX_LOG_G];
+    if (inverse) {
+        for (int q = 0; q < g; q++) {
+            DeviceScope scope(dev[q]);
+            MPC_TRY(scope.rc);
+            MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_IFFT, 1, st[q]));
+        }
+    }
+    MPC_TRY(cross_barrier(dev, st, ev_a, g));          // every block is ready to be read by every device
+    for (int r = 0; r < g; r++) {
+        DeviceScope scope(dev[r]);
+        MPC_TRY(scope.rc);
+        MPC_TRY(ntt_cross_launch(blocks, 0, log_n, log_g, (size_t)r * slice, slice, kind, st[r]));
+    }
+    MPC_TRY(cross_barrier(dev, st, ev_b, g));          // every block received the stores of every device
+    if (!inverse) {
+        for (int q = 0; q < g; q++) {
+            DeviceScope scope(dev[q]);
+            MPC_TRY(scope.rc);
+            MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_FFT, 1, st[q]));
+        }
+        MPC_TRY(cross_barrier(dev, st, ev_c, g));      // the first device's stream now orders after the whole job
+    }
+    return MPC_CUDA_OK;
+}
+
+// natural block order <-> the transposed order the forward kinds produce: out[r][mm] = X[mm g + bitrev(r)].
+// to_transposed: device r gathers its strided elements from every natural block (32-byte peer reads);
+// from_transposed: device q gathers natural index q m + j from owner bitrev(j mod g), local j / g.
+struct ReorderArgs {
+    const Fr* src[1 << MAX_LOG_G];
+    Fr* dst;
+    size_t m;
+    uint32_t log_g, me, to_transposed;
+};
+
+__global__ void __launch_bounds__(256) k_ntt_reorder(ReorderArgs a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.m) return;
+    const uint32_t g = 1u << a.log_g;
+    if (a.to_transposed) {
+        size_t nat = i * g + bitrev(a.me, a.log_g);                   // natural index of out[me][i]
+        store_fe(a.dst + i, load_fe(a.src[nat / a.m] + nat % a.m));
+    } else {
+        size_t nat = (size_t)a.me * a.m + i;                           // natural index of out[me][i]
+        store_fe(a.dst + i, load_fe(a.src[bitrev((uint32_t)(nat % g), a.log_g)] + nat / g));
+    }
+}
+
+int32_t ntt_reorder_sharded(Fr* const* in, Fr* const* out, const int32_t* dev_index, uint32_t log_n, uint32_t log_g,
+                            uint32_t to_transposed) {
+    MPC_ARG_CHECK(in && out && log_g >= 1 && log_g <= (uint32_t)MAX_LOG_G && log_n >= log_g && log_n <= MAX_LOG_N);
+    const int g = 1 << log_g;
+    int dev[1 << MAX_LOG_G];
+    cudaStream_t st[1 << MAX_LOG_G];
+    bool distinct = false;
+    for (int q = 0; q < g; q++) {
+        dev[q] = dev_index ? dev_index[q] : q;
+        MPC_ARG_CHECK(dev[q] >= 0 && dev[q] < device_list_size() && in[q] && out[q] && in[q] != out[q]);
+        if (dev[q] != dev[0]) distinct = true;
+    }
+    if (distinct) MPC_TRY(enable_peer_access());
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(dev[q]);
+        MPC_TRY(scope.rc);
+        st[q] = scope.s;
+    }
+    Ev ev_a[1 << MAX_LOG_G], ev_b[1 << MAX_LOG_G];
+    MPC_TRY(cross_barrier(dev, st, ev_a, g));
+    const size_t m = (size_t)1 << (log_n - log_g);
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(dev[q]);
+        MPC_TRY(scope.rc);
+        ReorderArgs a;
+        for (int r = 0; r < g; r++) a.src[r] = in[r];
+        a.dst = out[q];
+        a.m = m; a.log_g = log_g; a.me = (uint32_t)q; a.to_transposed = to_transposed;
+        k_ntt_reorder<<<(unsigned)((m + 255) / 256), 256, 0, st[q]>>>(a);
+        MPC_KERNEL_CHECK();
+    }
+    return cross_barrier(dev, st, ev_b, g);
 }
 
 }  // namespace
@@ -471,6 +631,64 @@ int32_t mpc_cuda_ntt_cross_stage_dev(uint64_t* data, uint32_t log_n, uint32_t lo
     cudaStream_t s;
     MPC_TRY(enter(&s));
     return ntt_cross_dev((Fr*)data, log_n, log_g, slice_offset, slice_len, kind, pick_stream(stream, s));
+}
+
+int32_t mpc_cuda_ntt_fr_sharded_dev(uint64_t* const* blocks, const int32_t* dev_index, uint32_t log_n, uint32_t log_g,
+                                    uint32_t kind) {
+    MPC_TRY(enter(nullptr));
+    return ntt_sharded_dev((Fr* const*)blocks, dev_index, log_n, log_g, kind);
+}
+
+int32_t mpc_cuda_ntt_reorder_sharded_dev(uint64_t* const* in, uint64_t* const* out, const int32_t* dev_index,
+                                         uint32_t log_n, uint32_t log_g, uint32_t to_transposed) {
+    MPC_TRY(enter(nullptr));
+    return ntt_reorder_sharded((Fr* const*)in, (Fr* const*)out, dev_index, log_n, log_g, to_transposed);
+}
+
+// host vector, in-order in and out like mpc_cuda_ntt_fr, computed on 2^log_g devices: block q goes to device q
+// over its own PCIe link, the transform runs sharded, the blocks come back in natural order
+int32_t mpc_cuda_ntt_fr_sharded(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t log_g) {
+    MPC_TRY(enter(nullptr));
+    MPC_ARG_CHECK(data && kind <= MPC_CUDA_NTT_COSET_IFFT && log_n <= MAX_LOG_N && log_g <= (uint32_t)MAX_LOG_G);
+    if (log_g == 0) return mpc_cuda_ntt_fr(data, log_n, kind, 1);
+    MPC_ARG_CHECK(log_n >= 2 * log_g && (1 << log_g) <= device_list_size());
+    const int g = 1 << log_g;
+    const size_t m = (size_t)1 << (log_n - log_g);
+    const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
+    MPC_TRY(enable_peer_access());
+    Scratch sa[1 << MAX_LOG_G], sb[1 << MAX_LOG_G];
+    Fr *a[1 << MAX_LOG_G], *b[1 << MAX_LOG_G];
+    cudaStream_t st[1 << MAX_LOG_G];
+    Fr* host = (Fr*)data;
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(q);
+        MPC_TRY(scope.rc);
+        st[q] = scope.s;
+        MPC_TRY(sa[q].alloc(&a[q], m, st[q]));
+        MPC_TRY(sb[q].alloc(&b[q], m, st[q]));
+        MPC_CUDA_TRY(cudaMemcpyAsync(a[q], host + (size_t)q * m, m * sizeof(Fr), cudaMemcpyHostToDevice, st[q]));
+    }
+    Fr** work = a;
+    if (inverse) {          // the inverse kinds consume the transposed order
+        MPC_TRY(ntt_reorder_sharded(a, b, nullptr, log_n, log_g, 1));
+        work = b;
+    }
+    MPC_TRY(ntt_sharded_dev(work, nullptr, log_n, log_g, kind));
+    if (!inverse) {         // the forward kinds produce it
+        MPC_TRY(ntt_reorder_sharded(a, b, nullptr, log_n, log_g, 0));
+        work = b;
+    }
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(q);
+        MPC_TRY(scope.rc);
+        MPC_CUDA_TRY(cudaMemcpyAsync(host + (size_t)q * m, work[q], m * sizeof(Fr), cudaMemcpyDeviceToHost, st[q]));
+    }
+    for (int q = 0; q < g; q++) {
+        DeviceScope scope(q);
+        MPC_TRY(scope.rc);
+        MPC_CUDA_TRY(cudaStreamSynchronize(st[q]));
+    }
+    return MPC_CUDA_OK;
 }
 
 int32_t mpc_cuda_ntt_fr(uint64_t* data, uint32_t log_n, uint32_t kind, uint32_t batch) {
@@ -495,10 +713,10 @@ int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n
     MPC_TRY(enter(&s0));
     cudaStream_t s = pick_stream(stream, s0);
     MPC_ARG_CHECK(data != nullptr && log_n <= MAX_LOG_N);
-    DomainCache* d;
-    MPC_TRY(ensure_tables(current_device_index(), 0, false, s, &d));
+    DomainCache dc;
+    MPC_TRY(ensure_tables(current_device_index(), 0, false, s, &dc));
     size_t n = (size_t)1 << log_n;
-    k_mul_const_dev<<<grid_for(n, 256, 8), 256, 0, s>>>((Fr*)data, d->consts + 96 + log_n, n);
+    k_mul_const_dev<<<grid_for(n, 256, 8), 256, 0, s>>>((Fr*)data, dc.consts + 96 + log_n, n);
     MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
 }

@@ -55,7 +55,8 @@ def device_count():
 
 
 # ----------------------------------------------------------------------------- diagnostics
-_FOPS = {"add": 0, "sub": 1, "mul": 2, "neg": 3, "inv": 4, "from_mont": 5, "to_mont": 6, "sqr": 7, "mul_narrow": 8}
+_FOPS = {"add": 0, "sub": 1, "mul": 2, "neg": 3, "inv": 4, "from_mont": 5, "to_mont": 6, "sqr": 7, "mul_narrow": 8,
+         "inv_euclid": 9}
 
 
 def field_op(field, op, a, b=None):
@@ -97,6 +98,8 @@ def beaver_combine(x, y, z, sx, oy, is_leader, spdz=False):
 
 def open_sum(parts):
     parts = _a(parts, 4)
+    if parts.ndim != 3:
+        raise ValueError("open_sum expects (parties, n, 4), got shape %s" % (parts.shape,))
     P, n = parts.shape[0], parts.shape[1]
     out = np.empty((n, 4), dtype=np.uint64)
     _lib.call("mpc_cuda_open_sum", _p(parts), C.c_uint32(P), _p(out), C.c_size_t(n))
@@ -150,6 +153,8 @@ def ntt(data, kind, batch=1):
 def divide_by_vanishing_on_coset(data):
     data = _a(data, 4).copy()
     n = data.size // 4
+    if n == 0 or n & (n - 1):
+        raise ValueError("domain size must be a power of two, got %d" % n)
     _lib.call("mpc_cuda_divide_by_vanishing_on_coset", _p(data), C.c_uint32(n.bit_length() - 1))
     return data
 
@@ -201,14 +206,20 @@ class BaseHandle:
             self.handle = 0
 
 
-def register_bases(bases_xy, inf=None, g2=False):
+def register_bases(bases_xy, inf=None, g2=False, parts=0):
+    """parts > 0: point-range sharding over the devices of the init list inside this process (range k on
+    device k mod n_dev); msm_handle / precompute then drive every part concurrently."""
     limbs = 24 if g2 else 12
     bases_xy = _a(bases_xy, limbs)
     n = bases_xy.size // limbs
     keep, pinf = _inf(inf, n)
     h = C.c_uint64(0)
-    _lib.call("mpc_cuda_msm_g2_register_bases" if g2 else "mpc_cuda_msm_g1_register_bases", _p(bases_xy), pinf,
-              C.c_size_t(n), C.byref(h))
+    if parts:
+        _lib.call("mpc_cuda_msm_g2_register_bases_sharded" if g2 else "mpc_cuda_msm_g1_register_bases_sharded",
+                  _p(bases_xy), pinf, C.c_size_t(n), C.c_uint32(parts), C.byref(h))
+    else:
+        _lib.call("mpc_cuda_msm_g2_register_bases" if g2 else "mpc_cuda_msm_g1_register_bases", _p(bases_xy), pinf,
+                  C.c_size_t(n), C.byref(h))
     return BaseHandle(h.value, n, g2)
 
 
@@ -282,10 +293,32 @@ def g2_generate(seed, n, first=0):
     return buf
 
 
-def register_bases_dev(buf, n):
+def register_bases_dev(buf, n, g2=False):
     h = C.c_uint64(0)
-    _lib.call("mpc_cuda_msm_g1_register_bases_dev", buf.u64(), C.c_size_t(n), C.byref(h))
-    return BaseHandle(h.value, n, False)
+    _lib.call("mpc_cuda_msm_g2_register_bases_dev" if g2 else "mpc_cuda_msm_g1_register_bases_dev", buf.u64(),
+              C.c_size_t(n), C.byref(h))
+    return BaseHandle(h.value, n, g2)
+
+
+def msm_handle_dev(handle, scalars_buf, n, offset=0, scalar_offset=0, out=None, stream=None):
+    """resident scalars -> Jacobian partial left on the device (DeviceBuffer of 3 x 6 (G1) / 3 x 12 (G2) limbs);
+    asynchronous on `stream` (None = the library's per-thread stream)"""
+    limbs = 36 if handle.g2 else 18
+    out = out or DeviceBuffer(limbs * 8)
+    sc = C.cast(C.c_void_p(scalars_buf.ptr.value + 32 * scalar_offset), u64p)
+    _lib.call("mpc_cuda_msm_g2_handle_dev" if handle.g2 else "mpc_cuda_msm_g1_handle_dev", C.c_uint64(handle.handle),
+              C.c_size_t(offset), sc, C.c_size_t(n), out.u64(), C.c_void_p(stream) if stream else None)
+    return out
+
+
+def sum_partials(buf, count, g2=False, stream=None):
+    """affine(sum of `count` Jacobian partials resident in `buf`)"""
+    limbs = 24 if g2 else 12
+    out = np.zeros(limbs, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    _lib.call("mpc_cuda_g2_sum_partials_dev" if g2 else "mpc_cuda_g1_sum_partials_dev", buf.u64(), C.c_uint32(count),
+              _p(out), C.byref(oinf), C.c_void_p(stream) if stream else None)
+    return out, oinf.value
 
 
 def launch_count():
@@ -303,6 +336,39 @@ def ntt_dev(ptr, log_n, kind, batch=1, stream=None):
     """in-place NTT of device-resident data (ptr: integer device address)"""
     _lib.call("mpc_cuda_ntt_fr_dev", C.cast(ptr, u64p), C.c_uint32(log_n), C.c_uint32(NTT_KIND[kind]), C.c_uint32(batch),
               C.c_void_p(stream) if stream else None)
+
+
+def ntt_sharded_dev(block_ptrs, log_n, kind, dev_index=None):
+    """one party's 2^log_n transform over len(block_ptrs) = 2^log_g blocks resident on the devices dev_index[q]
+    (None = q) of this process; asynchronous, ordered before later work on the first device's stream"""
+    g = len(block_ptrs)
+    log_g = g.bit_length() - 1
+    if (1 << log_g) != g:
+        raise ValueError("the number of blocks must be a power of two")
+    arr = (u64p * g)(*[C.cast(C.c_void_p(int(p)), u64p) for p in block_ptrs])
+    dv = (C.c_int32 * g)(*dev_index) if dev_index is not None else None
+    _lib.call("mpc_cuda_ntt_fr_sharded_dev", arr, dv, C.c_uint32(log_n), C.c_uint32(log_g), C.c_uint32(NTT_KIND[kind]))
+
+
+def ntt_reorder_sharded_dev(in_ptrs, out_ptrs, log_n, to_transposed, dev_index=None):
+    g = len(in_ptrs)
+    log_g = g.bit_length() - 1
+    a = (u64p * g)(*[C.cast(C.c_void_p(int(p)), u64p) for p in in_ptrs])
+    b = (u64p * g)(*[C.cast(C.c_void_p(int(p)), u64p) for p in out_ptrs])
+    dv = (C.c_int32 * g)(*dev_index) if dev_index is not None else None
+    _lib.call("mpc_cuda_ntt_reorder_sharded_dev", a, b, dv, C.c_uint32(log_n), C.c_uint32(log_g),
+              C.c_uint32(int(bool(to_transposed))))
+
+
+def ntt_sharded(data, kind, log_g):
+    """host vector in natural order in and out, computed on 2^log_g devices of this process"""
+    data = _a(data, 4).copy()
+    n = data.size // 4
+    log_n = n.bit_length() - 1
+    if n == 0 or (1 << log_n) != n:
+        raise ValueError("domain size must be a power of two, got %d" % n)
+    _lib.call("mpc_cuda_ntt_fr_sharded", _p(data), C.c_uint32(log_n), C.c_uint32(NTT_KIND[kind]), C.c_uint32(log_g))
+    return data
 
 
 def ntt_cross_stage_dev(ptr, log_n, log_g, slice_offset, slice_len, kind, stream=None):
