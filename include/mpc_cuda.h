@@ -57,7 +57,7 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value);
 uint64_t mpc_cuda_launch_count(void);
 /* Device time accumulated by the calling thread for a stage since the last read, and the number of
  * intervals; waits for the pending events.  Stages: "msm_total", "msm_sort", "msm_accumulate",
- * "msm_reduce", "ntt". */
+ * "msm_reduce", "msm_precompute", "ntt". */
 int32_t mpc_cuda_profile_read(const char* name, double* ms_total, uint64_t* count);
 const char* mpc_cuda_last_error(void);
 const char* mpc_cuda_version(void);
@@ -67,6 +67,11 @@ int32_t mpc_cuda_malloc(void** dptr, size_t bytes);
 int32_t mpc_cuda_free(void* dptr);
 int32_t mpc_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream);
 int32_t mpc_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream);
+int32_t mpc_cuda_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+/* extra streams on the calling thread's device, so independent `_dev` calls (the five MSMs of one proof,
+ * src/groth16.rs:106-160) overlap; NULL everywhere else means the library's own per-thread stream */
+int32_t mpc_cuda_stream_create(void** stream);
+int32_t mpc_cuda_stream_destroy(void* stream);
 int32_t mpc_cuda_stream_sync(void* stream);
 
 /* ---- Beaver multiplication, local halves ----------------------------------------------------
@@ -111,6 +116,7 @@ int32_t mpc_cuda_spdz_mac_check_dev(const uint64_t* vals, const uint64_t* macs, 
 #define MPC_CUDA_VEC_MUL 1
 #define MPC_CUDA_VEC_MUL_CONST 2
 #define MPC_CUDA_VEC_AXPY 3
+/* `out` may alias `a` (in place); it must not alias `b`. */
 int32_t mpc_cuda_vec_op(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c,
                         uint64_t* out, size_t n);
 int32_t mpc_cuda_vec_op_dev(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c_host,
@@ -158,18 +164,74 @@ int32_t mpc_cuda_divide_by_vanishing_on_coset(uint64_t* data, uint32_t log_n);
 int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n, void* stream);
 
 /* ---- fused witness map ---------------------------------------------------------------------
- * R1CStoQAP::witness_map on one party's local values (src/groth16.rs:278-303), additive shares.  The
- * vectors stay in HBM between the calls; only the masked values cross PCIe for the two opens, which stay
- * on mpc-net.  begin: a, b, c = the party's evaluations of the A, B, C polynomials over the domain
- * (2^log_n elements each), tx, ty = its Beaver triple shares; computes a' = coset_fft(ifft(a)) (same for
- * b, c) and returns masked_a = a' + tx, masked_b = b' + ty.  finish: tz = triple share, sx / oy = the
- * opened sums of masked_a / masked_b over the parties; returns this party's share of
- * h = coset_ifft((a'*b' - c') / Z_H).  finish always releases the state. */
+ * R1CStoQAP::witness_map on one party's local values (src/groth16.rs:240-307).  The vectors stay in HBM between
+ * the calls; only the masked values cross PCIe for the two opens, which stay on mpc-net.
+ * begin: a, b, c = the party's evaluations of the A, B, C polynomials over the domain (2^log_n elements each),
+ * tx, ty = its Beaver triple shares; computes a' = coset_fft(ifft(a)) (same for b, c) and returns
+ * masked_a = a' + tx, masked_b = b' + ty.  finish: tz = triple share, sx / oy = the opened sums of masked_a /
+ * masked_b over the parties; returns this party's share of h = coset_ifft((a'*b' - c') / Z_H) and releases the
+ * state.
+ * _ex, spdz = 1: SPDZ shares (mpc-algebra/src/share/spdz.rs:50-53,197-219): a, b, c, tx, ty, tz, masked_*, h
+ * hold two planes [sh | mac] of 2^log_n elements each; sx / oy stay one plane (opened values).
+ * _begin_r1cs: starts one step earlier, at the assignment: a = A z, b = B z, c = C z for the public CSR matrices
+ * registered with mpc_cuda_csr_register (evaluate_constraint, src/groth16.rs:205-234,263-270,289-293), with
+ * a[num_constraints .. num_constraints + num_inputs) = z[0 .. num_inputs) (:272-276) and zero padding to the
+ * domain; assignment = instance | witness values, `planes` x cols.
+ * _finish_dev: like finish, but h stays on the device (*h_dev, planes x n, valid until _release) so that it feeds
+ * the h_query MSM (src/groth16.rs:106) through mpc_cuda_msm_g1_handle_scalars_dev without crossing PCIe. */
 int32_t mpc_cuda_witness_map_begin(const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,
                                    const uint64_t* tx, const uint64_t* ty, uint64_t* masked_a, uint64_t* masked_b,
                                    uint64_t* state);
+int32_t mpc_cuda_witness_map_begin_ex(const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,
+                                      const uint64_t* tx, const uint64_t* ty, uint32_t spdz, uint64_t* masked_a,
+                                      uint64_t* masked_b, uint64_t* state);
+int32_t mpc_cuda_witness_map_begin_r1cs(uint64_t csr_a, uint64_t csr_b, uint64_t csr_c, const uint64_t* assignment,
+                                        size_t num_inputs, uint32_t log_n, const uint64_t* tx, const uint64_t* ty,
+                                        uint32_t spdz, uint64_t* masked_a, uint64_t* masked_b, uint64_t* state);
 int32_t mpc_cuda_witness_map_finish(uint64_t state, const uint64_t* tz, const uint64_t* sx, const uint64_t* oy,
                                     uint32_t is_leader, uint64_t* h_out);
+int32_t mpc_cuda_witness_map_finish_dev(uint64_t state, const uint64_t* tz, const uint64_t* sx, const uint64_t* oy,
+                                        uint32_t is_leader, uint64_t** h_dev);
+int32_t mpc_cuda_witness_map_release(uint64_t state);
+
+/* ---- linear steps either side of the path -----------------------------------
+ * f2: public sparse matrix x share vector = evaluate_constraint for every row (src/groth16.rs:205-234; Marlin:
+ * arkworks/marlin/src/ahp/prover.rs:258-278).  CSR: row_ptr[rows + 1] (u64), col[nnz] (u32 < cols), coeff[nnz]
+ * Montgomery Fr.  x holds `planes` vectors of `cols` elements (SPDZ: sh and mac planes), out `planes` x rows. */
+int32_t mpc_cuda_csr_register(const uint64_t* row_ptr, const uint32_t* col, const uint64_t* coeff_mont, size_t rows,
+                              size_t cols, uint64_t* handle);
+int32_t mpc_cuda_csr_release(uint64_t handle);
+int32_t mpc_cuda_csr_dims(uint64_t handle, size_t* rows, size_t* cols, size_t* nnz);
+int32_t mpc_cuda_csr_spmv(uint64_t handle, const uint64_t* x, uint32_t planes, uint64_t* out);
+int32_t mpc_cuda_csr_spmv_dev(uint64_t handle, const uint64_t* x_dev, size_t x_stride, uint32_t planes, uint64_t* out_dev,
+                              size_t out_stride, void* stream);
+/* f3: the bytes MpcSerNet::broadcast puts on the wire for a Vec<Fr> (mpc-algebra/src/channel.rs:12-28 ->
+ * arkworks/algebra/serialize/src/lib.rs:263-272, ff/src/fields/macros.rs:1-110): u64 LE length, then the 32 LE
+ * bytes of the canonical integer of every element; `out` / every payload holds 8 + 32 n bytes (8-byte aligned
+ * for the _dev entries).  _mask_serialize fuses the Beaver mask s + x (share/field.rs:108-117) with the
+ * conversion; _open_sum_deserialize reads the `n_parties` payloads received for a batch_open
+ * (share/additive.rs:125-131), back to back, and returns their sum in Montgomery form.  A length prefix other
+ * than n or an element >= r is an error (arkworks: SerializationError::InvalidData); the _dev entry reports it
+ * through flags_dev[0] (~0 = all valid, else 1 + index of the first bad element) and flags_dev[1] (1 = a bad
+ * length prefix). */
+int32_t mpc_cuda_fr_serialize(const uint64_t* vals_mont, size_t n, uint8_t* out);
+int32_t mpc_cuda_fr_deserialize(const uint8_t* in, size_t n, uint64_t* vals_mont);
+int32_t mpc_cuda_beaver_mask_serialize(const uint64_t* s, const uint64_t* x, size_t n, uint8_t* out);
+int32_t mpc_cuda_beaver_mask_serialize_dev(const uint64_t* s, const uint64_t* x /* NULL: no mask */, size_t n, uint8_t* out,
+                                           void* stream);
+int32_t mpc_cuda_open_sum_deserialize(const uint8_t* payloads, uint32_t n_parties, size_t n, uint64_t* out);
+int32_t mpc_cuda_open_sum_deserialize_dev(const uint8_t* payloads, uint32_t n_parties, size_t n, uint64_t* out,
+                                          uint64_t* flags_dev /*2*/, void* stream);
+/* f4: p(x) = q(x) (x - z) + rem for a public point z, on the local share values of p's n coefficients (low degree
+ * first): univariate_div_qr (mpc-algebra/src/wire/field.rs:1007-1065 -> share/additive.rs:154-162 ->
+ * arkworks/algebra/poly/src/polynomial/univariate/mod.rs:133-172) as KZG10::open divides by (x - point)
+ * (arkworks/poly-commit/src/kzg10/mod.rs:241-258).  q_out receives n - 1 coefficients (NULL: evaluation only),
+ * rem_out one element = p(z) (DensePolynomial::evaluate, univariate/dense.rs:53-75).  The reference truncates
+ * leading zero coefficients of q and drops a zero remainder; this returns the fixed-size arrays. */
+int32_t mpc_cuda_poly_div_linear(const uint64_t* coeffs, size_t n, const uint64_t* z_mont, uint64_t* q_out,
+                                 uint64_t* rem_out);
+int32_t mpc_cuda_poly_div_linear_dev(const uint64_t* coeffs, size_t n, const uint64_t* z_mont_host, uint64_t* q_out,
+                                     uint64_t* rem_out, void* stream);
 
 /* ---- share MSM ------------------------------------------------------------------------------
  * Msm::msm / AffineMsm::msm (mpc-algebra/src/share/msm.rs:6-9,33-37) =
@@ -221,6 +283,11 @@ int32_t mpc_cuda_g1_sum_partials_dev(const uint64_t* jac_dev /*count*18*/, uint3
                                      uint64_t out_xy[12], uint8_t* out_inf, void* stream);
 int32_t mpc_cuda_g2_sum_partials_dev(const uint64_t* jac_dev /*count*36*/, uint32_t count,
                                      uint64_t out_xy[24], uint8_t* out_inf, void* stream);
+/* scalars already on the device, affine result on the host (e.g. h left resident by mpc_cuda_witness_map_finish_dev) */
+int32_t mpc_cuda_msm_g1_handle_scalars_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
+                                           uint64_t out_xy[12], uint8_t* out_inf);
+int32_t mpc_cuda_msm_g2_handle_scalars_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
+                                           uint64_t out_xy[24], uint8_t* out_inf);
 /* whole-vector MSM over a sharded handle with the scalars already resident: scalars_mont_dev[k] is a pointer on
  * device k to the scalars of part k's point range (n/parts (+1) elements, same split as registration) */
 int32_t mpc_cuda_msm_g1_handle_sharded_dev(uint64_t handle, const uint64_t* const* scalars_mont_dev, uint32_t parts,
@@ -239,7 +306,8 @@ int32_t mpc_cuda_g2_generate_dev(uint64_t seed, size_t first, size_t n, uint64_t
 int32_t mpc_cuda_field_op(uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* Integer-pipe microbenchmark: returns achieved giga-ops/s of `iters` dependent instructions per
  * thread over a full-chip grid.  kind 0 = IMAD.U32 (32-bit), 1 = IMAD.WIDE.U32 with carry chain,
- * 2 = Fq Montgomery products (result in products/s), 3 = Fr Montgomery products. */
+ * 2 = Fq Montgomery products (result in products/s), 3 = Fr Montgomery products, 4 / 5 = the same through the
+ * 32-bit-column formulation, 6 = FP64 DFMA. */
 int32_t mpc_cuda_microbench(uint32_t kind, uint32_t iters, double* gops);
 
 #ifdef __cplusplus

@@ -316,3 +316,48 @@ def vec_op(op, a, b=None, c=None):
     lib().orc_vec_op(C.c_uint(VEC_OP[op]), _p(a), _p(b) if b is not None else None,
                      _p(c) if c is not None else None, _p(out), C.c_size_t(a.size // 4))
     return out
+
+
+# ----------------------------------------------------------------------------- next rows
+def spmv(row_ptr, col, coeff, x):
+    """evaluate_constraint (src/groth16.rs:205-234) per row of a public CSR matrix on local values x (m,4)"""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+    col = np.ascontiguousarray(col, dtype=np.uint32)
+    coeff, x = _a(coeff, 4), _a(x, 4)
+    rows = row_ptr.size - 1
+    out = np.zeros((rows, 4), dtype=np.uint64)
+    lib().orc_spmv(_p(row_ptr), col.ctypes.data_as(C.POINTER(C.c_uint32)), _p(coeff), C.c_size_t(rows), _p(x), _p(out))
+    return out
+
+
+def fr_vec_serialize(vals):
+    """the byte string MpcSerNet::broadcast sends for a Vec<Fr>: u64 LE length + 32 LE canonical bytes each"""
+    vals = _a(vals, 4)
+    n = vals.size // 4
+    out = np.zeros(8 + 32 * n, dtype=np.uint8)
+    lib().orc_fr_vec_serialize(_p(vals), C.c_size_t(n), _p8(out))
+    return out
+
+
+def fr_vec_deserialize(buf, n):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().orc_fr_vec_deserialize.restype = C.c_long
+    rc = lib().orc_fr_vec_deserialize(_p8(buf), C.c_size_t(n), _p(out))
+    if rc:
+        raise ValueError("deserialize failed: rc=%d" % rc)
+    return out
+
+
+def poly_div(num, den):
+    """divide_with_q_and_r (univariate/mod.rs:133-172): (quotient, remainder) with leading zeros truncated"""
+    num, den = _a(num, 4), _a(den, 4)
+    n = num.size // 4
+    q = np.zeros((max(n, 1), 4), dtype=np.uint64)
+    r = np.zeros((max(n, 1), 4), dtype=np.uint64)
+    ql, rl = C.c_size_t(0), C.c_size_t(0)
+    rc = lib().orc_poly_div(_p(num), C.c_size_t(n), _p(den), C.c_size_t(den.size // 4), _p(q), C.byref(ql), _p(r),
+                            C.byref(rl))
+    if rc:
+        raise ZeroDivisionError("Dividing by zero polynomial")
+    return q[:ql.value].copy(), r[:rl.value].copy()

@@ -24,6 +24,11 @@
  *               share/spdz.rs:31-47,135-146,177-219, wire/field.rs:44-63
  *   MSM glue    arkworks/algebra/ec/src/lib.rs:305-314, mpc-algebra/src/share/msm.rs:33-37,
  *               mpc-algebra/src/share/spdz.rs:482-488
+ *   R1CS rows   src/groth16.rs:205-234 (evaluate_constraint)
+ *   wire bytes  arkworks/algebra/serialize/src/lib.rs:263-272 ([T]: u64 length + items),
+ *               arkworks/algebra/ff/src/fields/macros.rs:1-110 (Fr = 32 LE bytes of into_repr; from_repr on read)
+ *   division    arkworks/algebra/poly/src/polynomial/univariate/mod.rs:133-172 (divide_with_q_and_r),
+ *               mpc-algebra/src/share/additive.rs:154-162, dense.rs:71-75 (horner_evaluate)
  */
 #include <stdint.h>
 #include <stddef.h>
@@ -716,6 +721,92 @@ EXPORT void orc_vec_op(unsigned op, const uint64_t *a, const uint64_t *b, const 
         }
         memcpy(out + 4 * i, r.l, 32);
     }
+}
+
+/* ================================================================== exported: next rows */
+/* f2 — evaluate_constraint (src/groth16.rs:205-234) for every row of a public CSR matrix against one party's
+ * assignment values: sum += coeff.is_one() ? val : val * coeff.  Linear, so on local share values it yields
+ * the party's share of the row. */
+EXPORT void orc_spmv(const uint64_t *row_ptr, const uint32_t *col, const uint64_t *coeff, size_t rows,
+                     const uint64_t *x, uint64_t *out) {
+    fr_t one;
+    fr_one(&one);
+    for (size_t r = 0; r < rows; r++) {
+        fr_t sum;
+        fr_zero(&sum);
+        for (uint64_t k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+            const fr_t *c = (const fr_t *)coeff + k, *v = (const fr_t *)x + col[k];
+            if (fr_eq(c, &one)) fr_add(&sum, &sum, v);
+            else { fr_t t; fr_mul(&t, v, c); fr_add(&sum, &sum, &t); }
+        }
+        memcpy(out + 4 * r, sum.l, 32);
+    }
+}
+
+/* f3 — CanonicalSerialize of a Vec<Fr> as MpcSerNet::broadcast sends it (mpc-algebra/src/channel.rs:12-28):
+ * u64 LE length, then 32 LE bytes of the canonical integer per element.  out holds 8 + 32 n bytes. */
+EXPORT void orc_fr_vec_serialize(const uint64_t *mont, size_t n, uint8_t *out) {
+    uint64_t len = n;
+    memcpy(out, &len, 8);              /* x86-64 is little endian, as the wire format */
+    for (size_t i = 0; i < n; i++) {
+        uint64_t repr[4];
+        fr_from_mont(repr, (const fr_t *)mont + i);
+        memcpy(out + 8 + 32 * i, repr, 32);
+    }
+}
+
+/* returns 0 on success, 1 if the length prefix differs from n, 2 + index of the first element >= modulus
+ * (arkworks: from_repr fails -> SerializationError::InvalidData) */
+EXPORT long orc_fr_vec_deserialize(const uint8_t *in, size_t n, uint64_t *mont_out) {
+    uint64_t len;
+    memcpy(&len, in, 8);
+    if (len != n) return 1;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t repr[4];
+        memcpy(repr, in + 8 + 32 * i, 32);
+        if (fr_cmp_raw(repr, FR_MOD) >= 0) return 2 + (long)i;
+        fr_to_mont((fr_t *)mont_out + i, repr);
+    }
+    return 0;
+}
+
+/* f4 — DenseOrSparsePolynomial::divide_with_q_and_r (univariate/mod.rs:145-170) on plain coefficient vectors
+ * (for shares: the local values, additive.rs:154-162).  q_out has room for n_num elements, r_out for n_num;
+ * the lengths after arkworks' truncation of leading zeros are returned through q_len / r_len. */
+static size_t poly_trim(const fr_t *c, size_t n) {
+    while (n && fr_is_zero(&c[n - 1])) n--;
+    return n;
+}
+EXPORT int orc_poly_div(const uint64_t *num, size_t n_num, const uint64_t *den, size_t n_den, uint64_t *q_out,
+                        size_t *q_len, uint64_t *r_out, size_t *r_len) {
+    const fr_t *a = (const fr_t *)num, *d = (const fr_t *)den;
+    size_t na = poly_trim(a, n_num), nd = poly_trim(d, n_den);
+    *q_len = 0; *r_len = 0;
+    if (na == 0) return 0;                                   /* zero dividend: (0, 0) */
+    if (nd == 0) return -1;                                  /* "Dividing by zero polynomial" */
+    if (na < nd) { memcpy(r_out, num, na * 32); *r_len = na; return 0; }
+    size_t nq = na - nd + 1;
+    fr_t *q = (fr_t *)q_out, *rem = (fr_t *)r_out;
+    for (size_t i = 0; i < nq; i++) fr_zero(&q[i]);
+    memcpy(rem, a, na * 32);
+    size_t nr = na;
+    fr_t lead_inv;
+    fr_inv(&lead_inv, &d[nd - 1]);
+    while (nr != 0 && nr >= nd) {
+        fr_t cq;
+        fr_mul(&cq, &rem[nr - 1], &lead_inv);
+        size_t deg = nr - nd;
+        q[deg] = cq;
+        for (size_t i = 0; i < nd; i++) {
+            fr_t t;
+            fr_mul(&t, &cq, &d[i]);
+            fr_sub(&rem[deg + i], &rem[deg + i], &t);
+        }
+        nr = poly_trim(rem, nr);
+    }
+    *q_len = poly_trim(q, nq);
+    *r_len = nr;
+    return 0;
 }
 
 /* constants for tests */

@@ -1,0 +1,292 @@
+"""GPU parity for the rows either side of the NTT / MSM / Beaver kernels, the SPDZ
+witness map, the wire-level packing rules (a5, a12) and the end-to-end Groth16 prove sequence (a16 / x1), all
+against the same composition on the oracle.  Bit-exact."""
+import threading
+
+import numpy as np
+import pytest
+
+import helpers
+import pyref as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def H(pkg):
+    pkg.host.init()
+    pkg.host.set_party(0, 3)
+    return pkg.host
+
+
+def _same(a, b):
+    return np.array_equal(a[0], b[0]) and a[1] == b[1]
+
+
+# ----------------------------------------------------------------------------- f2: constraint rows
+@pytest.mark.parametrize("rows,cols", [(0, 3), (1, 1), (37, 50), (6574, 6580)])
+def test_spmv_matches_evaluate_constraint(H, orc, pkg, rows, cols):
+    for k, (row_ptr, col, coeff) in enumerate(helpers.synth_r1cs(pkg, 0x510 + rows, rows, cols)):
+        m = H.CsrMatrix(row_ptr, col, coeff, cols)
+        x = pkg.synth.fr_uniform(0x520 + k, cols)
+        assert np.array_equal(m.spmv(x), orc.spmv(row_ptr, col, coeff, x))
+        planes = np.stack([x, pkg.synth.fr_uniform(0x530 + k, cols)])          # SPDZ: sh and mac planes
+        got = m.spmv(planes)
+        assert np.array_equal(got[0], orc.spmv(row_ptr, col, coeff, planes[0]))
+        assert np.array_equal(got[1], orc.spmv(row_ptr, col, coeff, planes[1]))
+        m.release()
+
+
+def test_spmv_dense_rows_use_the_warp_kernel(H, orc, pkg):
+    rows, cols = 8, 4000
+    rng = np.random.default_rng(3)
+    row_ptr = (np.arange(rows + 1) * 1000).astype(np.uint64)
+    col = rng.integers(0, cols, 8000).astype(np.uint32)
+    coeff = pkg.synth.fr_uniform(0x540, 8000)
+    coeff[::3] = pkg.synth.FR_R_LIMBS
+    x = pkg.synth.fr_uniform(0x541, cols)
+    m = H.CsrMatrix(row_ptr, col, coeff, cols)
+    assert np.array_equal(m.spmv(x), orc.spmv(row_ptr, col, coeff, x))
+    m.release()
+    with pytest.raises(H.MpcCudaError):
+        H.CsrMatrix(row_ptr, col + np.uint32(cols), coeff, cols)                 # column index out of range
+
+
+# ----------------------------------------------------------------------------- f3: wire bytes
+@pytest.mark.parametrize("n", [0, 1, 5, 1000, 1 << 16])
+def test_serialize_matches_canonical_serialize(H, orc, pkg, n):
+    v = pkg.synth.fr_uniform(0x610 + n, n)
+    if n >= 5:
+        v[:4] = P.fr_to_mont_arr([0, 1, P.R_MOD - 1, 1 << 200])
+    wire = H.fr_serialize(v)
+    assert np.array_equal(wire, orc.fr_vec_serialize(v))
+    if n >= 5:      # the bytes are the canonical little-endian integers behind a u64 length
+        assert int.from_bytes(wire[:8].tobytes(), "little") == n
+        assert int.from_bytes(wire[8 + 64:8 + 96].tobytes(), "little") == P.R_MOD - 1
+    assert np.array_equal(H.fr_deserialize(wire, n), v)
+    assert np.array_equal(orc.fr_vec_deserialize(wire, n), v)
+    x = pkg.synth.fr_uniform(0x620 + n, n)
+    assert np.array_equal(H.beaver_mask_serialize(v, x), orc.fr_vec_serialize(orc.beaver_mask(v, x)))
+
+
+def test_open_sum_from_wire_payloads(H, orc, pkg):
+    n, parties = 3000, 3
+    shares = np.stack([pkg.synth.fr_uniform(0x630 + p, n) for p in range(parties)])
+    payloads = np.stack([orc.fr_vec_serialize(s) for s in shares])
+    assert np.array_equal(H.open_sum_deserialize(payloads, n), orc.open_sum(shares))
+    bad = payloads.copy()
+    bad[1, 8 + 32 * 7:8 + 32 * 8] = 0xFF                                        # element 7 of party 1 >= r
+    with pytest.raises(H.MpcCudaError) as e:
+        H.open_sum_deserialize(bad, n)
+    assert "element 7" in str(e.value)
+    with pytest.raises(ValueError):
+        orc.fr_vec_deserialize(bad[1], n)
+    bad = payloads.copy()
+    bad[2, 0] ^= 1                                                              # wrong length prefix
+    with pytest.raises(H.MpcCudaError):
+        H.open_sum_deserialize(bad, n)
+
+
+# ----------------------------------------------------------------------------- f4: division by (x - z)
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 4096, 4097, 70000, (1 << 20) + 5])
+def test_poly_div_linear_matches_divide_with_q_and_r(H, orc, pkg, n):
+    p = pkg.synth.fr_uniform(0x710 + (n & 0xFF), n)
+    z = pkg.synth.fr_uniform(0x720, 1)[0]
+    den = np.stack([orc.fr("neg", z[None])[0], pkg.synth.FR_R_LIMBS])          # x - z
+    q, rem = H.poly_div_linear(p, z)
+    eq, er = orc.poly_div(p, den)
+    assert np.array_equal(q[:len(eq)], eq) and not q[len(eq):].any()
+    assert np.array_equal(rem, er[0] if len(er) else np.zeros(4, dtype=np.uint64))
+    assert np.array_equal(rem, orc.horner(p, z))                                # remainder = p(z)
+    assert np.array_equal(H.poly_evaluate(p, z), rem)
+
+
+def test_poly_div_linear_edge_points(H, orc, pkg):
+    n = 1000
+    p = pkg.synth.fr_uniform(0x730, n)
+    one = pkg.synth.FR_R_LIMBS
+    for z in (np.zeros(4, dtype=np.uint64), one, P.fr_to_mont_arr([P.R_MOD - 1])[0]):
+        den = np.stack([orc.fr("neg", z[None])[0], one])
+        q, rem = H.poly_div_linear(p, z)
+        eq, er = orc.poly_div(p, den)
+        assert np.array_equal(q, eq)
+        assert np.array_equal(rem, er[0] if len(er) else np.zeros(4, dtype=np.uint64))
+    # exact division: p = (x - z) * q0 has remainder 0 (arkworks returns the empty remainder)
+    z = pkg.synth.fr_uniform(0x731, 1)[0]
+    q0 = pkg.synth.fr_uniform(0x732, 50)
+    prod = np.zeros((51, 4), dtype=np.uint64)
+    prod[1:] = q0
+    prod[:50] = orc.vec_op("sub", prod[:50], orc.vec_op("mul_const", q0, c=z))
+    q, rem = H.poly_div_linear(prod, z)
+    assert np.array_equal(q, q0) and not rem.any()
+    assert len(orc.poly_div(prod, np.stack([orc.fr("neg", z[None])[0], one]))[1]) == 0
+
+
+# ----------------------------------------------------------------------------- SPDZ witness map
+@pytest.mark.parametrize("log_n", [3, 12])
+def test_spdz_witness_map_three_parties(H, orc, pkg, log_n):
+    """[sh | mac] planes through mpc_cuda_witness_map_begin_ex / finish: both planes of the opened h equal the
+    plain witness_map of the opened inputs; MAC key 1 shared as (1, 0, 0) (share/spdz.rs:31-47)"""
+    S = pkg.synth
+    n, parties = 1 << log_n, 3
+    sh = [[S.fr_uniform(0x800 + 10 * p + k, n) for k in range(3)] for p in range(parties)]
+    mac = [[S.fr_uniform(0x900 + 10 * p + k, n) for k in range(3)] for p in range(parties)]
+    # make the macs consistent: sum_p mac_p = sum_p sh_p (key 1): fix party 0's mac plane
+    for k in range(3):
+        tot_sh = orc.open_sum(np.stack([sh[p][k] for p in range(parties)]))
+        rest = orc.open_sum(np.stack([mac[p][k] for p in range(1, parties)]))
+        mac[0][k] = orc.vec_op("sub", tot_sh, rest)
+    one, zero = np.tile(S.FR_R_LIMBS, (n, 1)), np.zeros((n, 4), dtype=np.uint64)
+    trip = [np.stack([one, one])] + [np.stack([zero, zero])] * (parties - 1)     # dummy triple, sh = mac = (1,0,0)
+    begun = [H.witness_map_begin(*(np.stack([sh[p][k], mac[p][k]]) for k in range(3)), trip[p], trip[p], spdz=True)
+             for p in range(parties)]
+    sx = H.open_sum(np.stack([bg[0][0] for bg in begun]))
+    oy = H.open_sum(np.stack([bg[1][0] for bg in begun]))
+    # the MAC check of the two opens (share/spdz.rs:185-189): sum_p (mac_share_p * val - mac_p) == 0
+    for val, idx in ((sx, 0), (oy, 1)):
+        dx = np.stack([H.spdz_mac_check(val, begun[p][idx][1], p == 0) for p in range(parties)])
+        assert not H.open_sum(dx).any()
+    hs = [H.witness_map_finish(begun[p][2], trip[p], sx, oy, p == 0) for p in range(parties)]
+    a, b, c = (orc.open_sum(np.stack([sh[p][k] for p in range(parties)])) for k in range(3))
+    a1, b1, c1 = (orc.ntt(orc.ntt(v, "ifft"), "coset_fft") for v in (a, b, c))
+    exp = orc.ntt(orc.divide_by_vanishing_on_coset(orc.vec_op("sub", orc.vec_op("mul", a1, b1), c1)), "coset_ifft")
+    assert np.array_equal(H.open_sum(np.stack([h[0] for h in hs])), exp)         # sh plane
+    assert np.array_equal(H.open_sum(np.stack([h[1] for h in hs])), exp)         # mac plane (key 1)
+    # per party the result equals the oracle's Beaver semantics on its planes
+    p = 1
+    a1p, b1p, c1p = (np.stack([orc.ntt(orc.ntt(v, "ifft"), "coset_fft") for v in (sh[p][k], mac[p][k])]) for k in range(3))
+    comb = orc.beaver_combine(trip[p], trip[p], trip[p], sx, oy, False, spdz=True)
+    for plane in range(2):
+        e = orc.ntt(orc.divide_by_vanishing_on_coset(orc.vec_op("sub", comb[plane], c1p[plane])), "coset_ifft")
+        assert np.array_equal(hs[p][plane], e)
+
+
+# ----------------------------------------------------------------------------- a5 / a12: Public / Shared packing
+def test_wire_rules_for_fft_and_msm(H, orc, pkg):
+    W, S = pkg.wire, pkg.synth
+    n = 1 << 8
+    pub = S.fr_uniform(0xA10, n)
+    # all-Public stays Public: the same plain transform on every party
+    for leader in (True, False):
+        out = W.fft(W.MpcVec.public(pub), "coset_fft", leader)
+        assert not out.shared.any() and np.array_equal(out.val, orc.ntt(pub, "coset_fft"))
+    # mixed vector: Public(x) counts as x on the leader and 0 elsewhere; the opened transform is the transform
+    # of the opened vector
+    tags = np.arange(n) % 3 != 0
+    shares = [S.fr_uniform(0xA20 + p, n) for p in range(3)]
+    opened_in = orc.open_sum(np.stack(shares))
+    opened_in[~tags] = pub[~tags]
+    outs = []
+    for p in range(3):
+        v = shares[p].copy()
+        v[~tags] = pub[~tags]
+        out = W.fft(W.MpcVec(v, tags), "ifft", p == 0)
+        assert out.shared.all()
+        outs.append(out.val)
+    assert np.array_equal(orc.open_sum(np.stack(outs)), orc.ntt(opened_in, "ifft"))
+    # SPDZ: Public(x) -> sh as above, mac = x * mac_share; planes transform independently
+    v = shares[1].copy()
+    v[~tags] = pub[~tags]
+    macs = S.fr_uniform(0xA30, n)
+    for leader in (True, False):
+        planes = W.force_shared(W.MpcVec(v, tags, macs), leader, True)
+        exp_sh, exp_mac = v.copy(), macs.copy()
+        exp_mac[~tags] = pub[~tags] if leader else 0
+        if not leader:
+            exp_sh[~tags] = 0
+        assert np.array_equal(planes[0], exp_sh) and np.array_equal(planes[1], exp_mac)
+        out = W.fft(W.MpcVec(v, tags, macs), "fft", leader, spdz=True)
+        assert np.array_equal(out.val, orc.ntt(exp_sh, "fft")) and np.array_equal(out.mac, orc.ntt(exp_mac, "fft"))
+    # MSM dispatch (wire/pairing.rs:714-777)
+    bases = orc.g1_generate(0xA40, n)
+    plain = orc.g1_msm(bases, pub)
+    lead = W.multi_scalar_mul(bases, W.MpcVec.public(pub), True)
+    other = W.multi_scalar_mul(bases, W.MpcVec.public(pub), False)
+    assert _same(lead.sh, plain) and other.sh[1] == 1                            # from_public: leader holds it
+    assert P.fq_from_mont_arr(other.sh[0].reshape(2, 6)) == [0, 1]
+    parts = []
+    for p in range(3):
+        v = shares[p].copy()
+        v[~tags] = pub[~tags]
+        parts.append(W.multi_scalar_mul(bases, W.MpcVec(v, tags), p == 0).sh)
+    acc = parts[0]
+    for q in parts[1:]:
+        acc = orc.g1_add(acc[0], q[0], acc[1], q[1])
+    assert _same(acc, orc.g1_msm(bases, opened_in))
+    sp = W.multi_scalar_mul(bases, W.MpcVec(v, tags, macs), False, spdz=True)     # SPDZ quirk: mac built from sh
+    assert _same(sp.sh, sp.mac)
+    empty = W.multi_scalar_mul(bases[:0], W.MpcVec.share(np.zeros((0, 4), dtype=np.uint64)), True)
+    assert empty.sh[1] == 1
+
+
+# ----------------------------------------------------------------------------- the whole prove sequence
+def _run_parties(fn, n_parties):
+    out, errs = [None] * n_parties, []
+
+    def runner(p):
+        try:
+            out[p] = fn(p)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+            raise
+
+    ts = [threading.Thread(target=runner, args=(p,)) for p in range(n_parties)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.parametrize("shape", ["run_groth16_zsh", "my_secret_input_circuit"])
+@pytest.mark.parametrize("zk", [False, True])
+def test_groth16_prove_sequence_three_parties(H, orc, pkg, shape, zk):
+    """create_proof (src/groth16.rs:68-183) for 3 parties as 3 threads (LocalTestNet), additive shares, dummy
+    triples: witness map from the assignment (SpMV on the device), the two opens as wire payloads, h resident into
+    the h_query MSM, 4 G1 + 1 G2 MSMs.  The opened proof must equal the oracle's plain prover on the opened
+    assignment, bit for bit.  Shapes: run_groth16.zsh's circuit (domain 8, MSMs < 32 points) and
+    MySecretInputCircuit (6574 constraints + 5 inputs -> domain 2^13)."""
+    G, S = pkg.groth16, pkg.synth
+    if shape == "run_groth16_zsh":
+        nc, ni, nv = 3, 2, 6
+    else:
+        nc, ni, nv = 6574, 5, 6600
+    parties = 3
+    mats = helpers.synth_r1cs(pkg, 0xB10 + nc, nc, nv)
+    log_n = max(nc + ni - 1, 0).bit_length()
+    pkarr = helpers.synth_proving_key(orc, 0xB20 + nc, nv, ni, 1 << log_n)
+    # shares of the assignment: the constant 1 and the public inputs are Public -> leader holds them
+    z_open = S.fr_uniform(0xB30, nv)
+    z_open[0] = S.FR_R_LIMBS
+    shares = [S.fr_uniform(0xB40 + p, nv) for p in range(parties)]
+    rest = orc.open_sum(np.stack(shares[1:]))
+    shares[0] = orc.vec_op("sub", z_open, rest)
+    for p in range(1, parties):
+        shares[p][:ni] = 0
+    shares[0][:ni] = z_open[:ni]
+    assert np.array_equal(orc.open_sum(np.stack(shares)), z_open)
+    r, s = (S.fr_uniform(0xB50, 2) if zk else np.zeros((2, 4), dtype=np.uint64))
+    nets = helpers.ThreadNet.make(parties)
+    ready = threading.Barrier(parties)
+    state = {}
+
+    def party(p):
+        H.set_party(p, parties)
+        H.set_device(0)
+        if p == 0:
+            state["pk"] = G.ProvingKey(**pkarr)
+            state["r1cs"] = G.R1CS(*mats, num_inputs=ni, num_vars=nv)
+        ready.wait()
+        return G.prove_party(state["pk"], state["r1cs"], shares[p], nets[p], r=r, s=s)
+
+    proofs = _run_parties(party, parties)
+    H.set_party(0, 3)
+    exp = helpers.oracle_groth16(orc, pkarr, mats, ni, z_open, log_n, r, s)
+    for key, add in (("a", orc.g1_add), ("b", orc.g2_add), ("c", orc.g1_add)):
+        acc = proofs[0][key]
+        for q in proofs[1:]:
+            acc = add(acc[0], q[key][0], acc[1], q[key][1])
+        assert _same(acc, exp[key]), key
+    state["pk"].release()
+    state["r1cs"].release()

@@ -442,3 +442,56 @@ def test_synth_sampler(pkg):
     zeros = (~w.any(axis=1)).sum()
     ones = (w == S.FR_R_LIMBS).all(axis=1).sum()
     assert 800 < zeros < 1200 and 800 < ones < 1200
+
+
+# ----------------------------------------------------------------------------- next rows: SpMV, wire bytes, division
+def test_oracle_spmv_serialize_division_against_bigints(orc, pkg):
+    """the oracle's restatements of evaluate_constraint, CanonicalSerialize for Vec<Fr> and
+    divide_with_q_and_r against plain Python integers"""
+    import helpers
+    S = pkg.synth
+    rows, cols = 40, 25
+    for row_ptr, col, coeff in helpers.synth_r1cs(pkg, 0x77, rows, cols):
+        x = S.fr_uniform(0x78, cols)
+        xi, ci = P.fr_from_mont_arr(x), P.fr_from_mont_arr(coeff)
+        exp = [sum(ci[k] * xi[col[k]] for k in range(int(row_ptr[r]), int(row_ptr[r + 1]))) % P.R_MOD for r in range(rows)]
+        assert P.fr_from_mont_arr(orc.spmv(row_ptr, col, coeff, x)) == exp
+    v = S.fr_uniform(0x79, 9)
+    wire = orc.fr_vec_serialize(v).tobytes()
+    assert int.from_bytes(wire[:8], "little") == 9
+    assert [int.from_bytes(wire[8 + 32 * i:40 + 32 * i], "little") for i in range(9)] == P.fr_from_mont_arr(v)
+    assert np.array_equal(orc.fr_vec_deserialize(np.frombuffer(wire, dtype=np.uint8), 9), v)
+    # p = q * d + r with deg r < deg d, for a linear and a cubic divisor
+    p = S.fr_uniform(0x7A, 30)
+    for d in (S.fr_uniform(0x7B, 2), S.fr_uniform(0x7C, 4)):
+        q, r = orc.poly_div(p, d)
+        pi, di, qi, ri = (P.fr_from_mont_arr(a) for a in (p, d, q, r))
+        assert len(qi) == len(pi) - len(di) + 1 and len(ri) < len(di)
+        back = [0] * len(pi)
+        for i, a in enumerate(qi):
+            for j, b in enumerate(di):
+                back[i + j] = (back[i + j] + a * b) % P.R_MOD
+        for i, a in enumerate(ri):
+            back[i] = (back[i] + a) % P.R_MOD
+        assert back == pi
+    q0, r0 = orc.poly_div(np.zeros((3, 4), dtype=np.uint64), p[:2])          # zero dividend -> (0, 0)
+    assert len(q0) == 0 and len(r0) == 0
+
+
+def test_oracle_groth16_composition_runs(orc, pkg):
+    """helpers.oracle_groth16 (the checker of the GPU prove sequence): r = s = 0 gives c = l_acc + h_acc and the
+    A element is linear in the assignment"""
+    import helpers
+    S = pkg.synth
+    nc, ni, nv, log_n = 3, 2, 6, 3
+    mats = helpers.synth_r1cs(pkg, 0x7D, nc, nv)
+    pkarr = helpers.synth_proving_key(orc, 0x7E, nv, ni, 1 << log_n)
+    z = S.fr_uniform(0x7F, nv)
+    zero = np.zeros(4, dtype=np.uint64)
+    out = helpers.oracle_groth16(orc, pkarr, mats, ni, z, log_n, zero, zero)
+    hq, hinf = pkarr["h_query"]
+    lq, linf = pkarr["l_query"]
+    h_acc = orc.g1_msm_naive(hq, out["h"][:len(hq)], inf=hinf)
+    l_acc = orc.g1_msm_naive(lq, z[ni:], inf=linf)
+    exp = orc.g1_add(h_acc[0], l_acc[0], h_acc[1], l_acc[1])
+    assert np.array_equal(out["c"][0], exp[0]) and out["c"][1] == exp[1]

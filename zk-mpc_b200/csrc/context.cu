@@ -331,6 +331,29 @@ int32_t mpc_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* st
     return MPC_CUDA_OK;
 }
 
+int32_t mpc_cuda_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, pick_stream(stream, s)));
+    return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_stream_create(void** stream) {
+    MPC_ARG_CHECK(stream != nullptr);
+    MPC_TRY(enter(nullptr));
+    cudaStream_t s;
+    MPC_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void*)s;
+    return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_stream_destroy(void* stream) {
+    MPC_ARG_CHECK(stream != nullptr);
+    MPC_TRY(enter(nullptr));
+    MPC_CUDA_TRY(cudaStreamDestroy((cudaStream_t)stream));
+    return MPC_CUDA_OK;
+}
+
 int32_t mpc_cuda_stream_sync(void* stream) {
     cudaStream_t s;
     MPC_TRY(enter(&s));

@@ -87,6 +87,22 @@ __global__ void __launch_bounds__(MB_THREADS) k_mb_wide(uint32_t iters, uint32_t
     if (acc == 0x12345678u) sink[0] = (uint32_t)acc;
 }
 
+// kind 6: FP64 fused multiply-add, MB_ILP independent chains per thread (is the DFMA pipe worth a 52-bit-limb
+// Montgomery product next to the IMAD.WIDE one?)
+__global__ void __launch_bounds__(MB_THREADS) k_mb_dfma(uint32_t iters, double a, double b, double* sink) {
+    double x[MB_ILP];
+#pragma unroll
+    for (int k = 0; k < MB_ILP; k++) x[k] = (double)(threadIdx.x + k);
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < MB_ILP; k++) x[k] = __fma_rz(x[k], a, b);
+    }
+    double acc = 0;
+#pragma unroll
+    for (int k = 0; k < MB_ILP; k++) acc += x[k];
+    if (acc == 0.12345) sink[0] = acc;
+}
+
 // kinds 2..5: Montgomery products, one dependent chain per thread
 template <class F, bool NARROW>
 __global__ void __launch_bounds__(MB_THREADS) k_mb_mul(uint32_t iters, const F* __restrict__ in, F* __restrict__ out) {
@@ -108,7 +124,7 @@ int32_t mpc_cuda_field_op(uint32_t field, uint32_t op, const uint64_t* a, const 
 int32_t mpc_cuda_microbench(uint32_t kind, uint32_t iters, double* gops) {
     cudaStream_t s;
     MPC_TRY(enter(&s));
-    MPC_ARG_CHECK(kind <= 5 && iters >= 1 && gops);
+    MPC_ARG_CHECK(kind <= 6 && iters >= 1 && gops);
     const DeviceInfo* d = current_device_info();
     int blocks = d->sm_count * 8;
     Scratch sin, sout;
@@ -135,6 +151,7 @@ int32_t mpc_cuda_microbench(uint32_t kind, uint32_t iters, double* gops) {
             case 1: k_mb_wide<<<blocks, MB_THREADS, 0, s>>>(iters, 0x9e3779b1u, 0x85ebca6bu, sink); per_thread = (double)iters * 12; break;
             case 2: k_mb_mul<Fq, false><<<blocks, MB_THREADS, 0, s>>>(iters, (const Fq*)buf, (Fq*)sink); per_thread = iters; break;
             case 3: k_mb_mul<Fr, false><<<blocks, MB_THREADS, 0, s>>>(iters, (const Fr*)buf, (Fr*)sink); per_thread = iters; break;
+            case 6: k_mb_dfma<<<blocks, MB_THREADS, 0, s>>>(iters, 1.0000001, 0.5, (double*)sink); per_thread = (double)iters * MB_ILP; break;
             case 4: k_mb_mul<Fq, true><<<blocks, MB_THREADS, 0, s>>>(iters, (const Fq*)buf, (Fq*)sink); per_thread = iters; break;
             default: k_mb_mul<Fr, true><<<blocks, MB_THREADS, 0, s>>>(iters, (const Fr*)buf, (Fr*)sink); per_thread = iters; break;
         }

@@ -74,12 +74,12 @@ __global__ void __launch_bounds__(EW_THREADS) k_mac_check(const Fr* __restrict__
     }
 }
 
+// `out` may be `a` (in place): neither is declared restrict and `a` is read through the coherent path
 template <int OP>
-__global__ void __launch_bounds__(EW_THREADS) k_vec_op(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr c,
-                                                       Fr* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(EW_THREADS) k_vec_op(const Fr* a, const Fr* __restrict__ b, Fr c, Fr* out, size_t n) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Fr va = load_fe_ro(a + i);
+        Fr va = load_fe(a + i);
         Fr r;
         if (OP == MPC_CUDA_VEC_SUB) r = sub(va, load_fe_ro(b + i));
         else if (OP == MPC_CUDA_VEC_MUL) r = mul(va, load_fe_ro(b + i));

@@ -66,6 +66,21 @@ int32_t handle_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_
                        1, (uint32_t*)out_jac_dev, nullptr, nullptr, pick_stream(stream, s), &tbl);
 }
 
+// resident scalars (e.g. h left on the device by the fused witness map), affine result on the host
+template <class F>
+int32_t handle_scalars_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n, uint64_t* out_xy,
+                           uint8_t* out_inf, bool g2) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_ARG_CHECK(out_xy && out_inf && (n == 0 || scalars_mont_dev));
+    BaseSnap v;
+    MPC_TRY(registry_find(handle, g2, offset, n, &v));
+    MPC_ARG_CHECK(v.ref->parts.empty());
+    TableRef tbl = table_of(v, offset);
+    return msm_emit<F>((const Affine<F>*)v.bases + offset, v.inf ? v.inf + offset : nullptr, (const Fr*)scalars_mont_dev, n,
+                       0, nullptr, out_xy, out_inf, s, &tbl);
+}
+
 template <class F>
 int32_t sum_partials(const uint64_t* jac_dev, uint32_t count, uint64_t* out_xy, uint8_t* out_inf, void* stream) {
     constexpr int N = sizeof(F) / 4;
@@ -141,6 +156,11 @@ int32_t mpc_cuda_msm_g1_handle_dev(uint64_t handle, size_t offset, const uint64_
     return handle_dev<Fq>(handle, offset, scalars_mont_dev, n, out_jac_dev, stream, false);
 }
 
+int32_t mpc_cuda_msm_g1_handle_scalars_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
+                                           uint64_t out_xy[12], uint8_t* out_inf) {
+    return handle_scalars_dev<Fq>(handle, offset, scalars_mont_dev, n, out_xy, out_inf, false);
+}
+
 int32_t mpc_cuda_msm_g1_handle_sharded_dev(uint64_t handle, const uint64_t* const* scalars_mont_dev, uint32_t parts,
                                            uint64_t out_xy[12], uint8_t* out_inf) {
     return handle_sharded_dev<Fq>(handle, scalars_mont_dev, parts, out_xy, out_inf, false);
@@ -191,6 +211,11 @@ int32_t mpc_cuda_msm_g2_handle(uint64_t handle, size_t offset, const uint64_t* s
 int32_t mpc_cuda_msm_g2_handle_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
                                    uint64_t* out_jac_dev, void* stream) {
     return handle_dev<Fq2>(handle, offset, scalars_mont_dev, n, out_jac_dev, stream, true);
+}
+
+int32_t mpc_cuda_msm_g2_handle_scalars_dev(uint64_t handle, size_t offset, const uint64_t* scalars_mont_dev, size_t n,
+                                           uint64_t out_xy[24], uint8_t* out_inf) {
+    return handle_scalars_dev<Fq2>(handle, offset, scalars_mont_dev, n, out_xy, out_inf, true);
 }
 
 int32_t mpc_cuda_g2_sum_partials_dev(const uint64_t* jac_dev, uint32_t count, uint64_t out_xy[24], uint8_t* out_inf,

@@ -378,25 +378,188 @@ def ntt_cross_stage_dev(ptr, log_n, log_g, slice_offset, slice_len, kind, stream
 
 
 # ----------------------------------------------------------------------------- fused witness map
-def witness_map_begin(a, b, c, tx, ty):
+def _planes(v, spdz):
+    """(n,4) additive or (2,n,4) SPDZ [sh, mac] -> contiguous array, n"""
+    v = _a(v, 4)
+    if spdz:
+        if v.ndim != 3 or v.shape[0] != 2:
+            raise ValueError("SPDZ share vectors are (2, n, 4) = [sh plane, mac plane], got %s" % (v.shape,))
+        return v, v.shape[1]
+    if v.ndim != 2:
+        raise ValueError("additive share vectors are (n, 4), got %s" % (v.shape,))
+    return v, v.shape[0]
+
+
+class WitnessMapState:
+    """handle of a begun witness_map: remembers the domain size so finish can validate its inputs"""
+
+    def __init__(self, state, n, spdz):
+        self.state, self.n, self.spdz = state, n, spdz
+        self.h_ptr = None
+
+    def release(self):
+        if self.state:
+            _lib.call("mpc_cuda_witness_map_release", C.c_uint64(self.state))
+            self.state = 0
+
+
+def witness_map_begin(a, b, c, tx, ty, spdz=False):
     """first half of R1CStoQAP::witness_map (src/groth16.rs:278-285) on the device; returns
-    (masked_a, masked_b, state) — the masked vectors are what the party broadcasts for the two opens"""
-    a, b, c, tx, ty = (_a(v, 4) for v in (a, b, c, tx, ty))
-    n = a.size // 4
+    (masked_a, masked_b, state) — the masked vectors are what the party broadcasts for the two opens.
+    spdz: every vector is (2,n,4) = [sh, mac] planes (mpc-algebra/src/share/spdz.rs:50-53)."""
+    (a, n), (b, _), (c, _), (tx, _), (ty, _) = (_planes(v, spdz) for v in (a, b, c, tx, ty))
     log_n = n.bit_length() - 1
-    if (1 << log_n) != n or any(v.shape != a.shape for v in (b, c, tx, ty)):
+    if n == 0 or (1 << log_n) != n or any(v.shape != a.shape for v in (b, c, tx, ty)):
         raise ValueError("witness_map needs five equal power-of-two vectors")
     ma, mb = np.empty_like(a), np.empty_like(a)
     st = C.c_uint64(0)
-    _lib.call("mpc_cuda_witness_map_begin", _p(a), _p(b), _p(c), C.c_uint32(log_n), _p(tx), _p(ty), _p(ma), _p(mb),
+    _lib.call("mpc_cuda_witness_map_begin_ex", _p(a), _p(b), _p(c), C.c_uint32(log_n), _p(tx), _p(ty),
+              C.c_uint32(int(bool(spdz))), _p(ma), _p(mb), C.byref(st))
+    return ma, mb, WitnessMapState(st.value, n, bool(spdz))
+
+
+def witness_map_begin_r1cs(csr_a, csr_b, csr_c, assignment, num_inputs, log_n, tx, ty, spdz=False):
+    """the same from the assignment: a = A z, b = B z, c = C z on the device (evaluate_constraint,
+    src/groth16.rs:205-234,263-276,289-293); assignment = instance | witness local values, (cols,4) or (2,cols,4)"""
+    z, cols = _planes(assignment, spdz)
+    (tx, n), (ty, _) = _planes(tx, spdz), _planes(ty, spdz)
+    if n != 1 << log_n or ty.shape != tx.shape or cols != csr_a.cols:
+        raise ValueError("witness_map_begin_r1cs: triple planes must have 2^log_n elements and the assignment %d" % csr_a.cols)
+    ma, mb = np.empty_like(tx), np.empty_like(tx)
+    st = C.c_uint64(0)
+    _lib.call("mpc_cuda_witness_map_begin_r1cs", C.c_uint64(csr_a.handle), C.c_uint64(csr_b.handle), C.c_uint64(csr_c.handle),
+              _p(z), C.c_size_t(num_inputs), C.c_uint32(log_n), _p(tx), _p(ty), C.c_uint32(int(bool(spdz))), _p(ma), _p(mb),
               C.byref(st))
-    return ma, mb, st.value
+    return ma, mb, WitnessMapState(st.value, n, bool(spdz))
+
+
+def _finish_args(state, tz, sx, oy):
+    if not isinstance(state, WitnessMapState) or not state.state:
+        raise MpcCudaError("witness_map state already consumed")
+    (tz, n), sx, oy = _planes(tz, state.spdz), _a(sx, 4), _a(oy, 4)
+    if n != state.n or sx.shape != (state.n, 4) or oy.shape != (state.n, 4):
+        raise ValueError("witness_map_finish: tz / sx / oy must match the begun domain of %d elements" % state.n)
+    return tz, sx, oy
 
 
 def witness_map_finish(state, tz, sx, oy, is_leader):
     """second half (src/groth16.rs:285-303): Beaver combine, - c, / Z_H on the coset, coset iFFT"""
-    tz, sx, oy = _a(tz, 4), _a(sx, 4), _a(oy, 4)
+    tz, sx, oy = _finish_args(state, tz, sx, oy)
     h = np.empty_like(tz)
-    _lib.call("mpc_cuda_witness_map_finish", C.c_uint64(state), _p(tz), _p(sx), _p(oy),
+    st, state.state = state.state, 0            # finish always releases the state
+    _lib.call("mpc_cuda_witness_map_finish", C.c_uint64(st), _p(tz), _p(sx), _p(oy),
               C.c_uint32(int(bool(is_leader))), _p(h))
     return h
+
+
+def witness_map_finish_dev(state, tz, sx, oy, is_leader):
+    """like witness_map_finish, but h stays on the device: returns its device address (planes x n elements,
+    valid until state.release()) for mpc_cuda_msm_g1_handle_scalars_dev / msm_handle_dev"""
+    tz, sx, oy = _finish_args(state, tz, sx, oy)
+    ptr = u64p()
+    _lib.call("mpc_cuda_witness_map_finish_dev", C.c_uint64(state.state), _p(tz), _p(sx), _p(oy),
+              C.c_uint32(int(bool(is_leader))), C.byref(ptr))
+    state.h_ptr = C.cast(ptr, C.c_void_p).value
+    return state.h_ptr
+
+
+def msm_handle_scalars_dev(handle, scalars_ptr, n, offset=0):
+    """scalars resident at device address `scalars_ptr`, affine result + infinity flag on the host"""
+    limbs = 24 if handle.g2 else 12
+    out = np.zeros(limbs, dtype=np.uint64)
+    oinf = C.c_uint8(0)
+    _lib.call("mpc_cuda_msm_g2_handle_scalars_dev" if handle.g2 else "mpc_cuda_msm_g1_handle_scalars_dev",
+              C.c_uint64(handle.handle), C.c_size_t(offset), C.cast(C.c_void_p(int(scalars_ptr)), u64p), C.c_size_t(n),
+              _p(out), C.byref(oinf))
+    return out, oinf.value
+
+
+# ----------------------------------------------------------------------------- linear steps (SURVEY 8 f2-f4)
+class CsrMatrix:
+    """a public sparse matrix kept resident (the A, B, C matrices of the R1CS, Marlin's index matrices)"""
+
+    def __init__(self, row_ptr, col, coeff, cols):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        col = np.ascontiguousarray(col, dtype=np.uint32)
+        coeff = _a(coeff, 4)
+        if row_ptr.ndim != 1 or row_ptr.size < 1 or col.size != int(row_ptr[-1]) or coeff.size // 4 != col.size:
+            raise ValueError("malformed CSR arrays")
+        self.rows, self.cols, self.nnz = row_ptr.size - 1, int(cols), int(col.size)
+        h = C.c_uint64(0)
+        _lib.call("mpc_cuda_csr_register", _p(row_ptr), col.ctypes.data_as(C.POINTER(C.c_uint32)), _p(coeff),
+                  C.c_size_t(self.rows), C.c_size_t(self.cols), C.byref(h))
+        self.handle = h.value
+
+    def spmv(self, x):
+        """rows of evaluate_constraint on local values: x (cols,4) -> (rows,4); (planes,cols,4) -> (planes,rows,4)"""
+        x = _a(x, 4)
+        planes = 1 if x.ndim == 2 else x.shape[0]
+        if x.shape[-2] != self.cols:
+            raise ValueError("vector length %d != matrix columns %d" % (x.shape[-2], self.cols))
+        out = np.empty(x.shape[:-2] + (self.rows, 4), dtype=np.uint64)
+        _lib.call("mpc_cuda_csr_spmv", C.c_uint64(self.handle), _p(x), C.c_uint32(planes), _p(out))
+        return out
+
+    def release(self):
+        if self.handle:
+            _lib.call("mpc_cuda_csr_release", C.c_uint64(self.handle))
+            self.handle = 0
+
+
+def fr_serialize(vals):
+    """CanonicalSerialize of a Vec<Fr> (what MpcSerNet::broadcast sends): uint8 array of 8 + 32 n bytes"""
+    vals = _a(vals, 4)
+    n = vals.size // 4
+    out = np.zeros(8 + 32 * n, dtype=np.uint8)
+    _lib.call("mpc_cuda_fr_serialize", _p(vals), C.c_size_t(n), out.ctypes.data_as(u8p))
+    return out
+
+
+def fr_deserialize(buf, n):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    if buf.size != 8 + 32 * n:
+        raise ValueError("payload of %d bytes cannot hold %d elements" % (buf.size, n))
+    out = np.empty((n, 4), dtype=np.uint64)
+    _lib.call("mpc_cuda_fr_deserialize", buf.ctypes.data_as(u8p), C.c_size_t(n), _p(out))
+    return out
+
+
+def beaver_mask_serialize(s, x):
+    """wire payload of the masked vector s + x (share/field.rs:108-117 + channel.rs:12-28) in one pass"""
+    s, x = _a(s, 4), _a(x, 4)
+    if s.shape != x.shape:
+        raise ValueError("shape mismatch")
+    n = s.size // 4
+    out = np.zeros(8 + 32 * n, dtype=np.uint8)
+    _lib.call("mpc_cuda_beaver_mask_serialize", _p(s), _p(x), C.c_size_t(n), out.ctypes.data_as(u8p))
+    return out
+
+
+def open_sum_deserialize(payloads, n):
+    """batch_open's local half straight from the received wire payloads (one per party, 8 + 32 n bytes each)"""
+    payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+    if payloads.ndim != 2 or payloads.shape[1] != 8 + 32 * n:
+        raise ValueError("expected (parties, %d) bytes, got %s" % (8 + 32 * n, payloads.shape))
+    out = np.empty((n, 4), dtype=np.uint64)
+    _lib.call("mpc_cuda_open_sum_deserialize", payloads.ctypes.data_as(u8p), C.c_uint32(payloads.shape[0]), C.c_size_t(n),
+              _p(out))
+    return out
+
+
+def poly_div_linear(coeffs, z):
+    """(quotient, remainder) of p(x) / (x - z) on local share values: quotient (n-1,4), remainder (4,) = p(z)"""
+    coeffs, z = _a(coeffs, 4), _a(z, 4)
+    n = coeffs.size // 4
+    if n < 1:
+        raise ValueError("empty polynomial")
+    q = np.empty((n - 1, 4), dtype=np.uint64)
+    rem = np.empty(4, dtype=np.uint64)
+    _lib.call("mpc_cuda_poly_div_linear", _p(coeffs), C.c_size_t(n), _p(z), _p(q) if n > 1 else None, _p(rem))
+    return q, rem
+
+
+def poly_evaluate(coeffs, z):
+    coeffs, z = _a(coeffs, 4), _a(z, 4)
+    rem = np.empty(4, dtype=np.uint64)
+    _lib.call("mpc_cuda_poly_div_linear", _p(coeffs), C.c_size_t(coeffs.size // 4), _p(z), None, _p(rem))
+    return rem
