@@ -1,41 +1,19 @@
-//! Thin binding of `include/mpc_cuda.h`.  Safe wrappers take the reference's own types
+//! Thin binding of `include/mpc_cuda.h`.  `ffi` (generated from the header by tools/gen_rust_ffi.py) declares
+//! every function of the C ABI; the safe wrappers below take the reference's own types
 //! (`ark_bls12_377::{Fr, G1Affine, G2Affine}`), marshal them to Montgomery u64 limbs — the in-memory
 //! representation of `Fp256.0.0` / `Fp384.0.0` — and panic on a non-zero status, mirroring the
-//! `assert!`/`unwrap` convention of the code they replace.
+//! `assert!`/`unwrap` convention of the code they replace.  Every wrapper asserts that its slices have the
+//! lengths the C side will read.
 //!
-//! Source only: this repository's build container has no Rust toolchain, so the crate is not compiled
-//! there; the same ABI is driven by `zk-mpc_b200/host.py` (ctypes) in the tests.
+//! UNCOMPILED SKETCH: this repository's build container has no Rust toolchain, so the crate has never been
+//! compiled and its field accessors / constructors are unverified against the reference's arkworks fork.
+//! The same ABI is driven by `zk-mpc_b200/host.py` (ctypes) and `tests/c_abi/abi_check.c` (C) in the tests.
 use ark_bls12_377::{Fq, Fq2, Fr, G1Affine, G2Affine};
 use ark_ec::AffineCurve;
 use ark_ff::{Fp256, Fp384, Zero};
 use std::os::raw::c_char;
 
-#[allow(non_camel_case_types)]
-pub mod ffi {
-    use std::os::raw::{c_char, c_void};
-    extern "C" {
-        pub fn mpc_cuda_init(devices: *const i32, n_dev: i32) -> i32;
-        pub fn mpc_cuda_set_party(party_id: u32, n_parties: u32) -> i32;
-        pub fn mpc_cuda_last_error() -> *const c_char;
-        pub fn mpc_cuda_msm_g1(bases_xy: *const u64, inf: *const u8, scalars_mont: *const u64, n: usize,
-                               out_xy: *mut u64, out_inf: *mut u8) -> i32;
-        pub fn mpc_cuda_msm_g2(bases_xy: *const u64, inf: *const u8, scalars_mont: *const u64, n: usize,
-                               out_xy: *mut u64, out_inf: *mut u8) -> i32;
-        pub fn mpc_cuda_msm_g1_register_bases(bases_xy: *const u64, inf: *const u8, n: usize, handle: *mut u64) -> i32;
-        pub fn mpc_cuda_msm_g1_handle(handle: u64, offset: usize, scalars_mont: *const u64, n: usize,
-                                      out_xy: *mut u64, out_inf: *mut u8) -> i32;
-        pub fn mpc_cuda_msm_release_bases(handle: u64) -> i32;
-        pub fn mpc_cuda_ntt_fr(data: *mut u64, log_n: u32, kind: u32, batch: u32) -> i32;
-        pub fn mpc_cuda_divide_by_vanishing_on_coset(data: *mut u64, log_n: u32) -> i32;
-        pub fn mpc_cuda_beaver_mask(s: *const u64, x: *const u64, out: *mut u64, n: usize) -> i32;
-        pub fn mpc_cuda_beaver_combine(x: *const u64, y: *const u64, z: *const u64, sx: *const u64, oy: *const u64,
-                                       out: *mut u64, n: usize, is_leader: u32, spdz: u32) -> i32;
-        pub fn mpc_cuda_open_sum(parts: *const u64, n_parties: u32, out: *mut u64, n: usize) -> i32;
-        pub fn mpc_cuda_spdz_mac_check(vals: *const u64, macs: *const u64, out: *mut u64, n: usize, is_leader: u32) -> i32;
-        pub fn mpc_cuda_vec_op(op: u32, a: *const u64, b: *const u64, c: *const u64, out: *mut u64, n: usize) -> i32;
-        pub fn mpc_cuda_stream_sync(stream: *mut c_void) -> i32;
-    }
-}
+pub mod ffi;
 
 fn check(rc: i32) {
     if rc != 0 {
@@ -55,39 +33,82 @@ pub fn set_party(party_id: u32, n_parties: u32) { check(unsafe { ffi::mpc_cuda_s
 #[inline] fn fr_limbs(v: &[Fr]) -> Vec<u64> { v.iter().flat_map(|f| (f.0).0).collect() }
 #[inline] fn fr_from(l: &[u64]) -> Fr { Fp256::new(ark_ff::BigInteger256([l[0], l[1], l[2], l[3]])) }
 #[inline] fn fq_from(l: &[u64]) -> Fq { Fp384::new(ark_ff::BigInteger384([l[0], l[1], l[2], l[3], l[4], l[5]])) }
+#[inline] fn frs_from(l: &[u64]) -> Vec<Fr> { l.chunks_exact(4).map(fr_from).collect() }
+
+fn g1_limbs(bases: &[G1Affine]) -> (Vec<u64>, Vec<u8>) {
+    let mut xy = Vec::with_capacity(12 * bases.len());
+    let mut inf = Vec::with_capacity(bases.len());
+    for b in bases { xy.extend_from_slice(&(b.x.0).0); xy.extend_from_slice(&(b.y.0).0); inf.push(b.infinity as u8); }
+    (xy, inf)
+}
+fn g2_limbs(bases: &[G2Affine]) -> (Vec<u64>, Vec<u8>) {
+    let mut xy = Vec::with_capacity(24 * bases.len());
+    let mut inf = Vec::with_capacity(bases.len());
+    for b in bases {
+        for c in [&b.x.c0, &b.x.c1, &b.y.c0, &b.y.c1] { xy.extend_from_slice(&(c.0).0); }
+        inf.push(b.infinity as u8);
+    }
+    (xy, inf)
+}
+fn g1_from(out: &[u64; 12], inf: u8) -> G1Affine {
+    if inf != 0 { G1Affine::zero() } else { G1Affine::new(fq_from(&out[0..6]), fq_from(&out[6..12]), false) }
+}
+fn g2_from(out: &[u64; 24], inf: u8) -> G2Affine {
+    if inf != 0 { return G2Affine::zero(); }
+    G2Affine::new(Fq2::new(fq_from(&out[0..6]), fq_from(&out[6..12])), Fq2::new(fq_from(&out[12..18]), fq_from(&out[18..24])), false)
+}
 
 /// Drop-in body of `AffineMsm::<G1Affine>::msm` (mpc-algebra/src/share/msm.rs:33-37).
 pub fn msm_g1(bases: &[G1Affine], scalars: &[Fr]) -> G1Affine {
     let n = bases.len().min(scalars.len());                   // variable_base.rs:16-18
-    let mut xy = Vec::with_capacity(12 * n);
-    let mut inf = Vec::with_capacity(n);
-    for b in &bases[..n] { xy.extend_from_slice(&(b.x.0).0); xy.extend_from_slice(&(b.y.0).0); inf.push(b.infinity as u8); }
+    let (xy, inf) = g1_limbs(&bases[..n]);
     let sc = fr_limbs(&scalars[..n]);
+    assert_eq!(xy.len(), 12 * n); assert_eq!(inf.len(), n); assert_eq!(sc.len(), 4 * n);
     let (mut out, mut oinf) = ([0u64; 12], 0u8);
     check(unsafe { ffi::mpc_cuda_msm_g1(xy.as_ptr(), inf.as_ptr(), sc.as_ptr(), n, out.as_mut_ptr(), &mut oinf) });
-    if oinf != 0 { G1Affine::zero() } else { G1Affine::new(fq_from(&out[0..6]), fq_from(&out[6..12]), false) }
+    g1_from(&out, oinf)
 }
 
 /// Same over G2 (`b_g2_query`, src/groth16.rs:160).
 pub fn msm_g2(bases: &[G2Affine], scalars: &[Fr]) -> G2Affine {
     let n = bases.len().min(scalars.len());
-    let mut xy = Vec::with_capacity(24 * n);
-    let mut inf = Vec::with_capacity(n);
-    for b in &bases[..n] {
-        for c in [&b.x.c0, &b.x.c1, &b.y.c0, &b.y.c1] { xy.extend_from_slice(&(c.0).0); }
-        inf.push(b.infinity as u8);
-    }
+    let (xy, inf) = g2_limbs(&bases[..n]);
     let sc = fr_limbs(&scalars[..n]);
+    assert_eq!(xy.len(), 24 * n); assert_eq!(inf.len(), n); assert_eq!(sc.len(), 4 * n);
     let (mut out, mut oinf) = ([0u64; 24], 0u8);
     check(unsafe { ffi::mpc_cuda_msm_g2(xy.as_ptr(), inf.as_ptr(), sc.as_ptr(), n, out.as_mut_ptr(), &mut oinf) });
-    if oinf != 0 { return G2Affine::zero(); }
-    G2Affine::new(Fq2::new(fq_from(&out[0..6]), fq_from(&out[6..12])), Fq2::new(fq_from(&out[12..18]), fq_from(&out[18..24])), false)
+    g2_from(&out, oinf)
 }
+
+/// A CRS vector kept resident (pk.*_query, powers_of_g); `parts > 0` shards it over that many GPUs of the process.
+pub struct G1Bases { handle: u64, len: usize }
+impl G1Bases {
+    pub fn register(bases: &[G1Affine], parts: u32, precompute: bool) -> Self {
+        let (xy, inf) = g1_limbs(bases);
+        let mut handle = 0u64;
+        check(unsafe {
+            if parts > 0 { ffi::mpc_cuda_msm_g1_register_bases_sharded(xy.as_ptr(), inf.as_ptr(), bases.len(), parts, &mut handle) }
+            else { ffi::mpc_cuda_msm_g1_register_bases(xy.as_ptr(), inf.as_ptr(), bases.len(), &mut handle) }
+        });
+        if precompute { check(unsafe { ffi::mpc_cuda_msm_g1_precompute(handle, 0) }); }
+        G1Bases { handle, len: bases.len() }
+    }
+    /// MSM over `bases[offset .. offset + scalars.len()]`
+    pub fn msm(&self, offset: usize, scalars: &[Fr]) -> G1Affine {
+        assert!(offset <= self.len && scalars.len() <= self.len - offset);
+        let sc = fr_limbs(scalars);
+        let (mut out, mut oinf) = ([0u64; 12], 0u8);
+        check(unsafe { ffi::mpc_cuda_msm_g1_handle(self.handle, offset, sc.as_ptr(), scalars.len(), out.as_mut_ptr(), &mut oinf) });
+        g1_from(&out, oinf)
+    }
+}
+impl Drop for G1Bases { fn drop(&mut self) { unsafe { ffi::mpc_cuda_msm_release_bases(self.handle); } } }
 
 /// In-place transform of a vector already resized to the domain size (radix2/mod.rs:99-114).
 pub fn ntt_in_place(v: &mut [Fr], kind: u32) {
-    assert!(v.len().is_power_of_two());
+    assert!(v.len().is_power_of_two() && kind <= COSET_IFFT);
     let mut l = fr_limbs(v);
+    assert_eq!(l.len(), 4 * v.len());
     check(unsafe { ffi::mpc_cuda_ntt_fr(l.as_mut_ptr(), v.len().trailing_zeros(), kind, 1) });
     for (o, c) in v.iter_mut().zip(l.chunks_exact(4)) { *o = fr_from(c); }
 }
@@ -95,15 +116,47 @@ pub fn ntt_in_place(v: &mut [Fr], kind: u32) {
 /// Local half of `FieldShare::batch_mul` after the two opens (share/field.rs:118-128); additive layout.
 pub fn beaver_combine(x: &[Fr], y: &[Fr], z: &[Fr], sx: &[Fr], oy: &[Fr], is_leader: bool) -> Vec<Fr> {
     let n = sx.len();
+    assert_eq!(x.len(), n); assert_eq!(y.len(), n); assert_eq!(z.len(), n); assert_eq!(oy.len(), n);
     let mut out = vec![0u64; 4 * n];
-    check(unsafe { ffi::mpc_cuda_beaver_combine(fr_limbs(x).as_ptr(), fr_limbs(y).as_ptr(), fr_limbs(z).as_ptr(),
-        fr_limbs(sx).as_ptr(), fr_limbs(oy).as_ptr(), out.as_mut_ptr(), n, is_leader as u32, 0) });
-    out.chunks_exact(4).map(fr_from).collect()
+    let (lx, ly, lz, lsx, loy) = (fr_limbs(x), fr_limbs(y), fr_limbs(z), fr_limbs(sx), fr_limbs(oy));
+    check(unsafe { ffi::mpc_cuda_beaver_combine(lx.as_ptr(), ly.as_ptr(), lz.as_ptr(), lsx.as_ptr(), loy.as_ptr(),
+        out.as_mut_ptr(), n, is_leader as u32, 0) });
+    frs_from(&out)
 }
 
 /// `s_i + x_i` before the open (share/field.rs:108-117).
 pub fn beaver_mask(s: &[Fr], x: &[Fr]) -> Vec<Fr> {
+    assert_eq!(s.len(), x.len());
     let mut out = vec![0u64; 4 * s.len()];
-    check(unsafe { ffi::mpc_cuda_beaver_mask(fr_limbs(s).as_ptr(), fr_limbs(x).as_ptr(), out.as_mut_ptr(), s.len()) });
-    out.chunks_exact(4).map(fr_from).collect()
+    let (ls, lx) = (fr_limbs(s), fr_limbs(x));
+    check(unsafe { ffi::mpc_cuda_beaver_mask(ls.as_ptr(), lx.as_ptr(), out.as_mut_ptr(), s.len()) });
+    frs_from(&out)
+}
+
+/// The masked vector as the bytes `MpcSerNet::broadcast` sends (channel.rs:12-28): mask + serialise in one pass.
+pub fn beaver_mask_wire(s: &[Fr], x: &[Fr]) -> Vec<u8> {
+    assert_eq!(s.len(), x.len());
+    let mut out = vec![0u8; 8 + 32 * s.len()];
+    let (ls, lx) = (fr_limbs(s), fr_limbs(x));
+    check(unsafe { ffi::mpc_cuda_beaver_mask_serialize(ls.as_ptr(), lx.as_ptr(), s.len(), out.as_mut_ptr()) });
+    out
+}
+
+/// `batch_open`'s local half from the received payloads, one per party (share/additive.rs:125-131).
+pub fn open_sum_wire(payloads: &[Vec<u8>], n: usize) -> Vec<Fr> {
+    let mut flat = Vec::with_capacity(payloads.len() * (8 + 32 * n));
+    for p in payloads { assert_eq!(p.len(), 8 + 32 * n); flat.extend_from_slice(p); }
+    let mut out = vec![0u64; 4 * n];
+    check(unsafe { ffi::mpc_cuda_open_sum_deserialize(flat.as_ptr(), payloads.len() as u32, n, out.as_mut_ptr()) });
+    frs_from(&out)
+}
+
+/// `(p / (x - z), p(z))` on local share values (share/additive.rs:154-162, kzg10/mod.rs:241-258).
+pub fn poly_div_linear(coeffs: &[Fr], z: &Fr) -> (Vec<Fr>, Fr) {
+    assert!(!coeffs.is_empty());
+    let n = coeffs.len();
+    let (lc, lz) = (fr_limbs(coeffs), fr_limbs(std::slice::from_ref(z)));
+    let (mut q, mut rem) = (vec![0u64; 4 * (n - 1)], [0u64; 4]);
+    check(unsafe { ffi::mpc_cuda_poly_div_linear(lc.as_ptr(), n, lz.as_ptr(), if n > 1 { q.as_mut_ptr() } else { std::ptr::null_mut() }, rem.as_mut_ptr()) });
+    (frs_from(&q), fr_from(&rem))
 }

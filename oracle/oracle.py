@@ -361,3 +361,44 @@ def poly_div(num, den):
     if rc:
         raise ZeroDivisionError("Dividing by zero polynomial")
     return q[:ql.value].copy(), r[:rl.value].copy()
+
+
+# ----------------------------------------------------------------------------- the whole prove sequence
+def groth16_prove(pkarr, mats, num_inputs, z, log_n, r, s, threads=8):
+    """create_proof (src/groth16.rs:68-183) on plain values through the oracle's own MSM / NTT / SpMV"""
+    n = 1 << log_n
+    nc = len(mats[0][0]) - 1
+    ev = []
+    for row_ptr, col, coeff in mats:
+        v = np.zeros((n, 4), dtype=np.uint64)
+        v[:nc] = spmv(row_ptr, col, coeff, z)
+        ev.append(v)
+    ev[0][nc:nc + num_inputs] = z[:num_inputs]                            # :272-276
+    a1, b1, c1 = (ntt(ntt(v, "ifft"), "coset_fft") for v in ev)
+    ab = vec_op("sub", vec_op("mul", a1, b1), c1)
+    h = ntt(divide_by_vanishing_on_coset(ab), "coset_ifft")
+    hq, hinf = pkarr["h_query"]
+    h_acc = g1_msm(hq, h[:len(hq)], inf=hinf, threads=threads)
+    lq, linf = pkarr["l_query"]
+    l_acc = g1_msm(lq, z[num_inputs:], inf=linf, threads=threads)
+    from_mont = lambda x: fr("from_mont", x[None])[0]
+
+    def coeff(msm, add, smul, query, vk_param, delta, k):
+        pts, inf = query
+        acc = smul(delta, from_mont(k))                                     # initial = delta * k
+        acc = add(acc[0], pts[0], acc[1], inf[0])                           # + query[0]
+        m = msm(pts[1:], z[1:], inf=inf[1:], threads=threads)
+        acc = add(acc[0], m[0], acc[1], m[1])
+        return add(acc[0], vk_param, acc[1], 0)
+
+    g_a = coeff(g1_msm, g1_add, g1_scalar_mul, pkarr["a_query"], pkarr["alpha_g1"], pkarr["delta_g1"], r)
+    g1_b = coeff(g1_msm, g1_add, g1_scalar_mul, pkarr["b_g1_query"], pkarr["beta_g1"], pkarr["delta_g1"], s)
+    g2_b = coeff(g2_msm, g2_add, g2_scalar_mul, pkarr["b_g2_query"], pkarr["beta_g2"], pkarr["delta_g2"], s)
+    rs = fr("neg", fr("mul", r[None], s[None]))[0]
+    t1 = g1_scalar_mul(g_a[0], from_mont(s), g_a[1])
+    t2 = g1_scalar_mul(g1_b[0], from_mont(r), g1_b[1])
+    t3 = g1_scalar_mul(pkarr["delta_g1"], from_mont(rs))
+    g_c = g1_add(t1[0], t2[0], t1[1], t2[1])
+    for t in (t3, l_acc, h_acc):
+        g_c = g1_add(g_c[0], t[0], g_c[1], t[1])
+    return {"a": g_a, "b": g2_b, "c": g_c, "h": h}

@@ -44,47 +44,15 @@ import threading
 
 
 def synth_r1cs(pkg, seed, num_constraints, num_vars, max_terms=4):
-    """three random public CSR matrices shaped like an R1CS: short rows, most coefficients 1, a few rows long"""
-    rng = np.random.default_rng(seed)
-    mats = []
-    for k in range(3):
-        lens = rng.integers(0, max_terms + 1, num_constraints)
-        if num_constraints > 4:
-            lens[rng.integers(0, num_constraints)] = min(num_vars, 200)         # one long row
-        row_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
-        nnz = int(row_ptr[-1])
-        col = rng.integers(0, num_vars, nnz).astype(np.uint32)
-        coeff = np.tile(pkg.synth.FR_R_LIMBS, (nnz, 1))
-        other = rng.random(nnz) < 0.3
-        coeff[other] = pkg.synth.fr_uniform(seed * 7 + k, int(other.sum()))
-        mats.append((row_ptr, col, coeff))
-    return mats
+    return pkg.synth.r1cs_matrices(seed, num_constraints, num_vars, max_terms)
 
 
 def synth_proving_key(orc, seed, num_vars, num_inputs, n):
-    """queries of the right lengths with a few infinity entries (variables with zero coefficient), as arrays"""
     import pyref as P
     g2gen, _ = P.g2_to_arr((P.G2_X, P.G2_Y))
-
-    def g1(k, count):
-        pts = orc.g1_generate(seed + k, count)
-        inf = np.zeros(count, dtype=np.uint8)
-        if count > 8:
-            inf[[3, count // 2]] = 1
-        return pts, inf
-
-    def g2(k, count):
-        pts = orc.g2_generate(g2gen, seed + k, count)
-        inf = np.zeros(count, dtype=np.uint8)
-        if count > 8:
-            inf[[5]] = 1
-        return pts, inf
-
-    singles = orc.g1_generate(seed + 99, 3)
-    singles2 = orc.g2_generate(g2gen, seed + 98, 2)
-    return dict(a_query=g1(1, num_vars), b_g1_query=g1(2, num_vars), b_g2_query=g2(3, num_vars), h_query=g1(4, n - 1),
-                l_query=g1(5, num_vars - num_inputs), alpha_g1=singles[0], beta_g1=singles[1], delta_g1=singles[2],
-                beta_g2=singles2[0], delta_g2=singles2[1])
+    import __graft_entry__ as ge
+    return ge.load_package().synth.proving_key_arrays(orc.g1_generate, lambda s, c: orc.g2_generate(g2gen, s, c), seed,
+                                                      num_vars, num_inputs, n)
 
 
 class ThreadNet:
@@ -112,40 +80,4 @@ class ThreadNet:
 
 
 def oracle_groth16(orc, pkarr, mats, num_inputs, z, log_n, r, s):
-    """create_proof (src/groth16.rs:68-183) on plain values through the oracle's own MSM / NTT / SpMV"""
-    n = 1 << log_n
-    nc = len(mats[0][0]) - 1
-    ev = []
-    for row_ptr, col, coeff in mats:
-        v = np.zeros((n, 4), dtype=np.uint64)
-        v[:nc] = orc.spmv(row_ptr, col, coeff, z)
-        ev.append(v)
-    ev[0][nc:nc + num_inputs] = z[:num_inputs]                            # :272-276
-    a1, b1, c1 = (orc.ntt(orc.ntt(v, "ifft"), "coset_fft") for v in ev)
-    ab = orc.vec_op("sub", orc.vec_op("mul", a1, b1), c1)
-    h = orc.ntt(orc.divide_by_vanishing_on_coset(ab), "coset_ifft")
-    hq, hinf = pkarr["h_query"]
-    h_acc = orc.g1_msm(hq, h[:len(hq)], inf=hinf, threads=8)
-    lq, linf = pkarr["l_query"]
-    l_acc = orc.g1_msm(lq, z[num_inputs:], inf=linf, threads=8)
-    from_mont = lambda x: orc.fr("from_mont", x[None])[0]
-
-    def coeff(msm, add, smul, query, vk_param, delta, k):
-        pts, inf = query
-        acc = smul(delta, from_mont(k))                                     # initial = delta * k
-        acc = add(acc[0], pts[0], acc[1], inf[0])                           # + query[0]
-        m = msm(pts[1:], z[1:], inf=inf[1:], threads=8)
-        acc = add(acc[0], m[0], acc[1], m[1])
-        return add(acc[0], vk_param, acc[1], 0)
-
-    g_a = coeff(orc.g1_msm, orc.g1_add, orc.g1_scalar_mul, pkarr["a_query"], pkarr["alpha_g1"], pkarr["delta_g1"], r)
-    g1_b = coeff(orc.g1_msm, orc.g1_add, orc.g1_scalar_mul, pkarr["b_g1_query"], pkarr["beta_g1"], pkarr["delta_g1"], s)
-    g2_b = coeff(orc.g2_msm, orc.g2_add, orc.g2_scalar_mul, pkarr["b_g2_query"], pkarr["beta_g2"], pkarr["delta_g2"], s)
-    rs = orc.fr("neg", orc.fr("mul", r[None], s[None]))[0]
-    t1 = orc.g1_scalar_mul(g_a[0], from_mont(s), g_a[1])
-    t2 = orc.g1_scalar_mul(g1_b[0], from_mont(r), g1_b[1])
-    t3 = orc.g1_scalar_mul(pkarr["delta_g1"], from_mont(rs))
-    g_c = orc.g1_add(t1[0], t2[0], t1[1], t2[1])
-    for t in (t3, l_acc, h_acc):
-        g_c = orc.g1_add(g_c[0], t[0], g_c[1], t[1])
-    return {"a": g_a, "b": g2_b, "c": g_c, "h": h}
+    return orc.groth16_prove(pkarr, mats, num_inputs, z, log_n, r, s)

@@ -62,3 +62,19 @@ def test_product_package_never_imports_the_oracle(built):
             assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
             assert not re.search(r"#include\s+[\"<].*oracle", text), f
             assert "libzkmpc_oracle" not in text, f
+
+
+def test_rust_ffi_block_covers_the_whole_header(built):
+    """bindings/rust/mpc-cuda/src/ffi.rs is generated from include/mpc_cuda.h (tools/gen_rust_ffi.py): it must
+    declare every function of the C ABI, and be up to date with the header"""
+    import re
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    ffi = open(os.path.join(root, "bindings", "rust", "mpc-cuda", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (mpc_cuda_\w+)\(", ffi))
+    assert declared == set(built._lib.declared_symbols())
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_rust_ffi
+    before = ffi
+    gen_rust_ffi.main()
+    assert open(gen_rust_ffi.OUT).read() == before, "ffi.rs is stale: run tools/gen_rust_ffi.py"

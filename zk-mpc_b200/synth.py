@@ -63,3 +63,60 @@ def fr_witness_like(seed, n):
 
 def bench_seed(log_n):
     return 0x5EED0000 + log_n
+
+
+# ----------------------------------------------------------------------------- synthetic Groth16 instances
+def r1cs_matrices(seed, num_constraints, num_vars, max_terms=4):
+    """three random public CSR matrices shaped like an R1CS: short rows, most coefficients 1, a few rows long"""
+    rng = np.random.default_rng(seed)
+    mats = []
+    for k in range(3):
+        lens = rng.integers(0, max_terms + 1, num_constraints)
+        if num_constraints > 4:
+            lens[rng.integers(0, num_constraints)] = min(num_vars, 200)         # one long row
+        row_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        nnz = int(row_ptr[-1])
+        col = rng.integers(0, num_vars, nnz).astype(np.uint32)
+        coeff = np.tile(FR_R_LIMBS, (nnz, 1))
+        other = rng.random(nnz) < 0.3
+        coeff[other] = fr_uniform(seed * 7 + k, int(other.sum()))
+        mats.append((row_ptr, col, coeff))
+    return mats
+
+
+def proving_key_arrays(g1_generate, g2_generate, seed, num_vars, num_inputs, n):
+    """queries of the right lengths with a few infinity entries (variables with zero coefficient do produce them,
+    SURVEY.md Appendix A).  g1_generate(seed, count) / g2_generate(seed, count) -> affine point arrays."""
+    def g1(k, count):
+        pts = g1_generate(seed + k, count)
+        inf = np.zeros(count, dtype=np.uint8)
+        if count > 8:
+            inf[[3, count // 2]] = 1
+        return pts, inf
+
+    def g2(k, count):
+        pts = g2_generate(seed + k, count)
+        inf = np.zeros(count, dtype=np.uint8)
+        if count > 8:
+            inf[[5]] = 1
+        return pts, inf
+
+    singles = g1_generate(seed + 99, 3)
+    singles2 = g2_generate(seed + 98, 2)
+    return dict(a_query=g1(1, num_vars), b_g1_query=g1(2, num_vars), b_g2_query=g2(3, num_vars), h_query=g1(4, n - 1),
+                l_query=g1(5, num_vars - num_inputs), alpha_g1=singles[0], beta_g1=singles[1], delta_g1=singles[2],
+                beta_g2=singles2[0], delta_g2=singles2[1])
+
+
+def additive_shares(seed, opened, parties, num_public, sub):
+    """split `opened` (m,4) into `parties` additive shares; the first num_public entries are Public values, i.e. held
+    by the leader with 0 elsewhere (from_public).  sub(a, b) = a - b on (m,4) arrays (a field subtraction)."""
+    shares = [fr_uniform(seed + p, opened.shape[0]) for p in range(parties)]
+    rest = np.zeros_like(opened)
+    for p in range(1, parties):
+        shares[p][:num_public] = 0
+    acc = opened.copy()
+    for p in range(1, parties):
+        acc = sub(acc, shares[p])
+    shares[0] = acc
+    return shares
