@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""NTT timings on the current GPU (device-resident data, profile events): ms per transform."""
+"""NTT timings on the current GPU (device-resident data, profile events): ms per transform, for the compile-time-shaped
+pass kernels and the generic one (option ntt_generic)."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
@@ -10,13 +11,16 @@ H.set_option("profile", 1)
 for log_n in [int(x) for x in sys.argv[1:]] or [16, 20, 22, 24]:
     n = 1 << log_n
     buf = H.DeviceBuffer(n * 32).upload(S.fr_uniform(log_n, n))
-    out = {}
-    for kind, name in ((0, "fft"), (1, "ifft"), (2, "coset_fft"), (3, "coset_ifft")):
-        for it in range(6):
-            L.call("mpc_cuda_ntt_fr_dev", buf.u64(), C.c_uint32(log_n), C.c_uint32(kind), C.c_uint32(1), None)
-            L.call("mpc_cuda_stream_sync", None)
-            if it == 1: H.profile_read("ntt")
-        t, cnt = H.profile_read("ntt")
-        out[name] = round(t / cnt, 4)
+    for mb in (0, 1):
+        H.set_option("ntt_generic", mb)
+        out = {}
+        for kind, name in ((0, "fft"), (1, "ifft"), (2, "coset_fft"), (3, "coset_ifft")):
+            for it in range(6):
+                L.call("mpc_cuda_ntt_fr_dev", buf.u64(), C.c_uint32(log_n), C.c_uint32(kind), C.c_uint32(1), None)
+                L.call("mpc_cuda_stream_sync", None)
+                if it == 1: H.profile_read("ntt")
+            t, cnt = H.profile_read("ntt")
+            out[name] = round(t / cnt, 4)
+        print(json.dumps({"log_n": log_n, "generic_kernel": mb, **out, "Melem_s_fft": round(n / out["fft"] / 1e3, 1)}), flush=True)
+    H.set_option("ntt_generic", 0)
     buf.free()
-    print(json.dumps({"log_n": log_n, **out, "Melem_s_fft": round(n / out["fft"] / 1e3, 1)}), flush=True)

@@ -873,14 +873,16 @@ constexpr int PRE_K = 4;
 
 template <class F>
 __global__ void __launch_bounds__(ACC_THREADS) k_precompute(const Affine<F>* __restrict__ bases,
-                                                            const uint8_t* __restrict__ inf, size_t n, uint32_t c,
-                                                            uint32_t nwin, Affine<F>* __restrict__ table,
-                                                            F* __restrict__ zs /* [nwin-1][n] */,
-                                                            F* __restrict__ prefix /* [nwin-1][n] */) {
+                                                            const uint8_t* __restrict__ inf, size_t n, size_t first,
+                                                            size_t count, uint32_t c, uint32_t nwin,
+                                                            Affine<F>* __restrict__ table,
+                                                            F* __restrict__ zs /* [nwin-1][count] */,
+                                                            F* __restrict__ prefix /* [nwin-1][count] */) {
+    // this launch covers bases [first, first + count); the scratch is indexed relative to `first`
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t i0 = t * PRE_K;
-    if (i0 >= n) return;
-    size_t i1 = i0 + PRE_K < n ? i0 + PRE_K : n;
+    size_t i0 = first + t * PRE_K;
+    if (i0 >= first + count) return;
+    size_t i1 = i0 + PRE_K < first + count ? i0 + PRE_K : first + count;
     F run = F::one();
     for (size_t i = i0; i < i1; i++) {
         Affine<F> pt = load_pod_ro(bases + i);
@@ -892,7 +894,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_precompute(const Affine<F>* __r
             for (uint32_t k = 0; k < c; k++) jac_dbl(acc);
             Affine<F> raw;
             raw.x = acc.x; raw.y = acc.y;
-            size_t slot = (size_t)(w - 1) * n + i;
+            size_t slot = (size_t)(w - 1) * count + (i - first);
             store_pod(table + (size_t)w * n + i, raw);
             store_pod(zs + slot, acc.z);
             store_pod(prefix + slot, run);          // product of every Z before this one
@@ -903,7 +905,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_precompute(const Affine<F>* __r
     for (size_t i = i1; i-- > i0;) {
         if (inf && inf[i]) continue;
         for (uint32_t w = nwin - 1; w >= 1; w--) {
-            size_t slot = (size_t)(w - 1) * n + i;
+            size_t slot = (size_t)(w - 1) * count + (i - first);
             F z = load_pod(zs + slot), pre = load_pod(prefix + slot);
             F zi = mul(invrun, pre);                // 1 / Z of this entry
             invrun = mul(invrun, z);
@@ -929,17 +931,22 @@ int32_t precompute_one(const BaseSnap& v, uint64_t handle, uint32_t window_bits,
     void* table = nullptr;
     MPC_CUDA_TRY(cudaMalloc(&table, (size_t)nwin * (v.n ? v.n : 1) * sizeof(Affine<F>)));
     if (v.n) {
+        // slices of 2^20 bases: the scratch (2 x (nwin - 1) field elements per base) stays ~1 GB however long the CRS
+        const size_t slice = std::min<size_t>(v.n, (size_t)1 << 20);
         Scratch sz, sp;
         F *zs, *prefix;
-        ProfileScope prof("msm_precompute", s);
-        if (sz.alloc(&zs, (size_t)(nwin - 1) * v.n, s) != MPC_CUDA_OK || sp.alloc(&prefix, (size_t)(nwin - 1) * v.n, s) != MPC_CUDA_OK) {
+        if (sz.alloc(&zs, (size_t)(nwin - 1) * slice, s) != MPC_CUDA_OK || sp.alloc(&prefix, (size_t)(nwin - 1) * slice, s) != MPC_CUDA_OK) {
             cudaFree(table);
             return MPC_CUDA_ERR_CUDA;
         }
-        size_t threads = (v.n + PRE_K - 1) / PRE_K;
-        k_precompute<F><<<(unsigned)((threads + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, s>>>(
-            (const Affine<F>*)v.bases, v.inf, v.n, c, nwin, (Affine<F>*)table, zs, prefix);
-        MPC_KERNEL_CHECK();
+        ProfileScope prof("msm_precompute", s);
+        for (size_t first = 0; first < v.n; first += slice) {
+            size_t count = std::min(slice, v.n - first);
+            size_t threads = (count + PRE_K - 1) / PRE_K;
+            k_precompute<F><<<(unsigned)((threads + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, s>>>(
+                (const Affine<F>*)v.bases, v.inf, v.n, first, count, c, nwin, (Affine<F>*)table, zs, prefix);
+            MPC_KERNEL_CHECK();
+        }
     }
     MPC_CUDA_TRY(cudaStreamSynchronize(s));
     if (handle) {

@@ -22,6 +22,10 @@
 
 using namespace mpc;
 
+namespace mpc {
+std::atomic<int64_t> g_opt_ntt_generic{0};      // 1: always run the generic pass kernel (A/B measurements, tests)
+}
+
 namespace {
 
 constexpr int NTT_MAX_DEG = 8;
@@ -86,23 +90,35 @@ struct PassArgs {
     uint32_t last, inverse;
 };
 
-DEV Fr sm_load(const uint32_t* sm, uint32_t E, uint32_t e) {
+// Tile element e lives at word swz(e) of each of the 8 limb planes.  The XOR swizzle makes every access pattern
+// of the kernel hit 32 distinct banks per warp: a warp touches elements whose index varies in 5 bit positions
+// {0,1} + three of {2..9} (contiguous runs of the load/store phases, the strided item sets of the radix-4 rounds
+// with half = 4, 2, 1, the radix-2 tail, the bit-reversed rows of the last store); bank bits 2..4 are b2^b5^b7,
+// b3^b5^b6^b8 and b4^b6^b9, whose restriction to each of those triples is invertible over GF(2).  swz is linear
+// over GF(2), so for an item whose four elements differ only in bits that are zero in e0,
+// swz(e0 + k*es) = swz(e0) ^ swz(k*es): one XOR per element.
+DEV uint32_t swz(uint32_t e) {
+    return e ^ (((e >> 5) & 1u) * 0xCu) ^ (((e >> 6) & 1u) * 0x18u) ^ (((e >> 7) & 1u) << 2) ^ (((e >> 8) & 1u) << 3) ^
+           (((e >> 9) & 1u) << 4);
+}
+// p = physical (swizzled) word index
+DEV Fr sm_load(const uint32_t* sm, uint32_t E, uint32_t p) {
     Fr r;
 #pragma unroll
-    for (int l = 0; l < 8; l++) r.v[l] = sm[l * E + e];
+    for (int l = 0; l < 8; l++) r.v[l] = sm[l * E + p];
     return r;
 }
-DEV void sm_store(uint32_t* sm, uint32_t E, uint32_t e, const Fr& a) {
+DEV void sm_store(uint32_t* sm, uint32_t E, uint32_t p, const Fr& a) {
 #pragma unroll
-    for (int l = 0; l < 8; l++) sm[l * E + e] = a.v[l];
+    for (int l = 0; l < 8; l++) sm[l * E + p] = a.v[l];
 }
 DEV uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? __brev(x) >> (32 - bits) : 0; }
 
 // one DIF butterfly: u' = u + v, v' = (u - v) * w^k with w = ω_l, read from the forward table of domain l;
 // inverse transforms use ω^-k = -ω^(2^(l-1) - k) (the sign is folded into the subtraction order)
-DEV void bfly(Fr& u, Fr& v, const Fr* __restrict__ tw, size_t k, uint32_t l, bool inverse) {
+DEV void bfly(Fr& u, Fr& v, const Fr* __restrict__ tw, uint32_t k, uint32_t l, bool inverse) {
     bool swap = inverse && k != 0;
-    if (swap) k = ((size_t)1 << (l - 1)) - k;
+    if (swap) k = (1u << (l - 1)) - k;
     Fr d = swap ? sub(v, u) : sub(u, v);
     u = add(u, v);
     v = l > 1 ? mul(d, load_fe_ro(tw + k)) : d;       // l == 1: the only twiddle is 1
@@ -111,96 +127,102 @@ DEV void bfly(Fr& u, Fr& v, const Fr* __restrict__ tw, size_t k, uint32_t l, boo
 // Every thread owns four rows of the tile and runs TWO stages on them in registers between
 // shared-memory exchanges (radix-4 step = 4 products, half the shared traffic and barriers of radix-2);
 // an odd stage count ends with one radix-2 stage.
+// DEG > 0: the tile shape (2^DEG rows x 4 columns, the shape of every pass of a transform of 2^12 or more
+// elements) is a compile-time constant, so the rounds unroll and the index algebra folds into immediates;
+// DEG = 0 is the generic kernel for the small shapes.
 constexpr int NTT_THREADS = 256;
-__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
+template <int DEG, int LAST>
+__global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS, DEG == 8 ? 3 : DEG == 7 ? 6 : DEG == 6 ? 12 : 3)
+    k_ntt_pass(PassArgs a) {
     extern __shared__ uint32_t sm[];
     const uint32_t t = threadIdx.x;
-    const uint32_t rows = 1u << a.deg, C = 1u << a.lc, E = rows << a.lc;
+    const uint32_t deg = DEG ? DEG : a.deg, lc = DEG ? NTT_LOG_C : a.lc;
+    const bool last = DEG ? LAST != 0 : a.last != 0;
+    const uint32_t rows = 1u << deg, C = 1u << lc, E = rows << lc;
+    const uint32_t log_t = a.log_n - a.s0 - deg;            // T = 2^log_t: distance of the tile's rows
+    const uint32_t T = 1u << log_t;
     const size_t n = (size_t)1 << a.log_n;
-    const size_t T = n >> (a.s0 + a.deg);
-    const size_t tile = blockIdx.x;
+    const uint32_t tile = blockIdx.x;
     const Fr* src = a.src + (size_t)blockIdx.y * n;
     Fr* dst = a.dst + (size_t)blockIdx.y * n;
     const bool inverse = a.inverse != 0;
 
     // tile origin: non-last: i = origin + j*T + c;  last: i = (hb + (bitrev(c) << (s0-lc))) * rows + j
-    size_t origin = 0, lo0 = 0, hb = 0;
-    if (!a.last) {
-        size_t tiles_per_hi = T >> a.lc;
-        size_t hi = tile / tiles_per_hi;
-        lo0 = (tile % tiles_per_hi) << a.lc;
-        origin = hi * (n >> a.s0) + lo0;
+    uint32_t origin = 0, lo0 = 0, hb = 0;
+    if (!last) {
+        uint32_t log_tiles_per_hi = log_t - lc;
+        uint32_t hi = tile >> log_tiles_per_hi;
+        lo0 = (tile & ((1u << log_tiles_per_hi) - 1)) << lc;
+        origin = (hi << (a.log_n - a.s0)) + lo0;
     } else {
-        hb = bitrev((uint32_t)(tile << a.lc), a.s0);
+        hb = bitrev(tile << lc, a.s0);
     }
 
-    // ---- load
+    // ---- load: tile slot e = (row j, column c); consecutive threads take consecutive slots
     for (uint32_t e = t; e < E; e += blockDim.x) {
-        uint32_t j, c;
-        size_t i;
-        if (!a.last) {
-            j = e >> a.lc; c = e & (C - 1);
-            i = origin + (size_t)j * T + c;
-        } else {
-            c = e >> a.deg; j = e & (rows - 1);
-            i = ((hb + ((size_t)bitrev(c, a.lc) << (a.s0 - a.lc))) << a.deg) + j;
-        }
+        const uint32_t j = e >> lc, c = e & (C - 1);
+        uint32_t i;
+        if (!last) i = origin + (j << log_t) + c;
+        else i = ((hb + (bitrev(c, lc) << (a.s0 - lc))) << deg) + j;     // 4 runs of 8 x 32 B per warp
         Fr x = load_fe(src + i);
         if (a.pre_lo) {
             x = mul(x, load_fe_ro(a.pre_lo + (i & ((1u << COSET_LO_BITS) - 1))));
             if (a.log_n > COSET_LO_BITS) x = mul(x, load_fe_ro(a.pre_hi + (i >> COSET_LO_BITS)));
         }
-        sm_store(sm, E, (j << a.lc) + c, x);
+        sm_store(sm, E, swz(e), x);
     }
     __syncthreads();
 
     // ---- radix-4 rounds: stages r (half = 2h) and r+1 (half = h) on rows base + {0, h, 2h, 3h}
     uint32_t r = 0;
-    for (; r + 2 <= a.deg; r += 2) {
-        const uint32_t hbits = a.deg - 2 - r, h = 1u << hbits;
+#pragma unroll
+    for (; r + 2 <= deg; r += 2) {
+        const uint32_t hbits = deg - 2 - r, h = 1u << hbits;
         const uint32_t l0 = a.log_n - a.s0 - r;
+        const uint32_t es = h << lc, s1 = swz(es), s2 = swz(2 * es), s3 = s1 ^ s2;
         for (uint32_t item = t; item < E / 4; item += blockDim.x) {
-            const uint32_t c = item & (C - 1), q = item >> a.lc;
-            const size_t lo = a.last ? 0 : lo0 + c;
+            const uint32_t c = item & (C - 1), q = item >> lc;
+            const uint32_t lo = last ? 0 : lo0 + c;
             const uint32_t qq = q & (h - 1);
-            const uint32_t e0 = ((((q >> hbits) << (hbits + 2)) | qq) << a.lc) + c, es = h << a.lc;
-            Fr x0 = sm_load(sm, E, e0), x1 = sm_load(sm, E, e0 + es), x2 = sm_load(sm, E, e0 + 2 * es),
-               x3 = sm_load(sm, E, e0 + 3 * es);
-            bfly(x0, x2, a.tw[r], (size_t)qq * T + lo, l0, inverse);
-            bfly(x1, x3, a.tw[r], (size_t)(qq + h) * T + lo, l0, inverse);
-            bfly(x0, x1, a.tw[r + 1], (size_t)qq * T + lo, l0 - 1, inverse);
-            bfly(x2, x3, a.tw[r + 1], (size_t)qq * T + lo, l0 - 1, inverse);
-            sm_store(sm, E, e0, x0);
-            sm_store(sm, E, e0 + es, x1);
-            sm_store(sm, E, e0 + 2 * es, x2);
-            sm_store(sm, E, e0 + 3 * es, x3);
+            const uint32_t p0 = swz(((((q >> hbits) << (hbits + 2)) | qq) << lc) + c);
+            Fr x0 = sm_load(sm, E, p0), x1 = sm_load(sm, E, p0 ^ s1), x2 = sm_load(sm, E, p0 ^ s2),
+               x3 = sm_load(sm, E, p0 ^ s3);
+            const uint32_t k = (qq << log_t) + lo;
+            bfly(x0, x2, a.tw[r], k, l0, inverse);
+            bfly(x1, x3, a.tw[r], k + (h << log_t), l0, inverse);
+            bfly(x0, x1, a.tw[r + 1], k, l0 - 1, inverse);
+            bfly(x2, x3, a.tw[r + 1], k, l0 - 1, inverse);
+            sm_store(sm, E, p0, x0);
+            sm_store(sm, E, p0 ^ s1, x1);
+            sm_store(sm, E, p0 ^ s2, x2);
+            sm_store(sm, E, p0 ^ s3, x3);
         }
         __syncthreads();
     }
     // ---- odd stage count: last stage of the pass (half = 1) pairs rows (2b, 2b+1)
-    if (r < a.deg) {
+    if (r < deg) {
         const uint32_t l0 = a.log_n - a.s0 - r;
         for (uint32_t item = t; item < E / 2; item += blockDim.x) {
-            const uint32_t c = item & (C - 1), bq = item >> a.lc;
-            const size_t lo = a.last ? 0 : lo0 + c;
-            const uint32_t e0 = ((2 * bq) << a.lc) + c, es = C;
-            Fr x0 = sm_load(sm, E, e0), x1 = sm_load(sm, E, e0 + es);
+            const uint32_t c = item & (C - 1), bq = item >> lc;
+            const uint32_t lo = last ? 0 : lo0 + c;
+            const uint32_t p0 = swz(((2 * bq) << lc) + c), p1 = p0 ^ swz(C);
+            Fr x0 = sm_load(sm, E, p0), x1 = sm_load(sm, E, p1);
             bfly(x0, x1, a.tw[r], lo, l0, inverse);
-            sm_store(sm, E, e0, x0);
-            sm_store(sm, E, e0 + es, x1);
+            sm_store(sm, E, p0, x0);
+            sm_store(sm, E, p1, x1);
         }
         __syncthreads();
     }
 
     // ---- store
     for (uint32_t e = t; e < E; e += blockDim.x) {
-        uint32_t j = e >> a.lc, cc = e & (C - 1);
-        if (!a.last) {
-            store_fe(dst + origin + (size_t)j * T + cc, sm_load(sm, E, e));
+        uint32_t j = e >> lc, cc = e & (C - 1);
+        if (!last) {
+            store_fe(dst + origin + (j << log_t) + cc, sm_load(sm, E, swz(e)));
         } else {
             // row j of the store is destination block j: source row bitrev(j)
-            Fr x = sm_load(sm, E, (bitrev(j, a.deg) << a.lc) + cc);
-            size_t d = ((size_t)j << a.s0) + (tile << a.lc) + cc;
+            Fr x = sm_load(sm, E, swz((bitrev(j, deg) << lc) + cc));
+            uint32_t d = (j << a.s0) + (tile << lc) + cc;
             if (a.scale) x = mul(x, load_fe_ro(a.scale));
             if (a.post_lo) {
                 x = mul(x, load_fe_ro(a.post_lo + (d & ((1u << COSET_LO_BITS) - 1))));
@@ -209,6 +231,21 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(PassArgs a) {
             store_fe(dst + d, x);
         }
     }
+}
+
+template <int DEG, int LAST>
+int32_t launch_pass(const PassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s) {
+    static bool configured[64] = {};                 // per device of the init list; benign race (idempotent call)
+    int dev = current_device_index();
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        // 16-32 KB tiles: let several CTAs share an SM (the default carveout fits one)
+        MPC_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<DEG, LAST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+        configured[dev] = true;
+    }
+    k_ntt_pass<DEG, LAST><<<grid, threads, smem, s>>>(a);
+    MPC_KERNEL_CHECK();
+    return MPC_CUDA_OK;
 }
 
 // n == 1: ifft / coset_ifft multiply by 1⁻¹ = 1, everything is the identity
@@ -240,9 +277,6 @@ int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s,
     DomainCache& d = g_cache[dev_index];
     bool dirty = false;
     if (!d.ready) {
-        // 32 KB tiles: let several CTAs share an SM (the default carveout fits one)
-        MPC_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
         MPC_CUDA_TRY(cudaMalloc((void**)&d.consts, 144 * sizeof(Fr)));
         MPC_CUDA_TRY(cudaMalloc((void**)&d.gen_pair, 2 * sizeof(Fr)));
         k_domain_consts<<<1, 64, 0, s>>>(fr_from_limbs(consts::FR_TWO_ADIC_ROOT), fr_from_limbs(consts::FR_TWO_INV),
@@ -348,8 +382,14 @@ int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStr
         MPC_ARG_CHECK(tiles < ((size_t)1 << 31) && batch < 65536);
         dim3 grid((unsigned)tiles, batch);
         uint32_t threads = E / 4 < 32 ? 32 : (E / 4 > NTT_THREADS ? NTT_THREADS : E / 4);
-        k_ntt_pass<<<grid, threads, (size_t)E * sizeof(Fr), s>>>(a);
-        MPC_KERNEL_CHECK();
+        const size_t smem = (size_t)E * sizeof(Fr);
+        const bool shaped = a.lc == (uint32_t)NTT_LOG_C && g_opt_ntt_generic.load(std::memory_order_relaxed) == 0;
+        int32_t rc;
+        if (shaped && deg == 8) rc = last ? launch_pass<8, 1>(a, grid, 256, smem, s) : launch_pass<8, 0>(a, grid, 256, smem, s);
+        else if (shaped && deg == 7) rc = last ? launch_pass<7, 1>(a, grid, 128, smem, s) : launch_pass<7, 0>(a, grid, 128, smem, s);
+        else if (shaped && deg == 6) rc = last ? launch_pass<6, 1>(a, grid, 64, smem, s) : launch_pass<6, 0>(a, grid, 64, smem, s);
+        else rc = launch_pass<0, 0>(a, grid, threads, smem, s);
+        MPC_TRY(rc);
         s0 += deg;
     }
     return MPC_CUDA_OK;

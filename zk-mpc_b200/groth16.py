@@ -97,78 +97,101 @@ def dummy_triple(n, is_leader):
     return v, v, v
 
 
-class _Streams:
-    def __init__(self, k):
-        self.ptrs = []
-        for _ in range(k):
+class ProverSession:
+    """Per-party working set reused across proofs of one circuit: the scalar buffers of the four MSMs, their
+    Jacobian partials and four streams.  Allocating these per proof costs more than the kernels at Groth16 sizes
+    (cudaMalloc / cudaFree synchronise the device, which also stalls the other parties' streams)."""
+
+    def __init__(self, pk, r1cs):
+        if pk.num_vars != r1cs.num_vars:
+            raise ValueError("proving key and R1CS disagree on the number of variables")
+        if pk.n_h > r1cs.n or pk.n_l != r1cs.num_vars - r1cs.num_inputs:
+            raise ValueError("h_query / l_query do not fit the domain / witness size")
+        self.pk, self.r1cs = pk, r1cs
+        m = r1cs.num_vars - 1
+        self.za = H.DeviceBuffer((m + 3) * 32)
+        self.zb = H.DeviceBuffer((m + 3) * 32)
+        self.lh = H.DeviceBuffer((pk.n_l + pk.n_h) * 32)
+        self.parts = [H.DeviceBuffer(18 * 8), H.DeviceBuffer(18 * 8), H.DeviceBuffer(36 * 8), H.DeviceBuffer(18 * 8)]
+        self.streams = []
+        for _ in range(4):
             p = C.c_void_p(0)
             _lib.call("mpc_cuda_stream_create", C.byref(p))
-            self.ptrs.append(p)
+            self.streams.append(p)
 
     def close(self):
-        for p in self.ptrs:
+        for p in self.streams:
             _lib.call("mpc_cuda_stream_destroy", p)
-        self.ptrs = []
+        self.streams = []
+        for b in [self.za, self.zb, self.lh] + self.parts:
+            b.free()
+
+    def prove(self, assignment, net, triple=None, r=None, s=None):
+        """One party's share of the proof (a, b, c) from its share of the full assignment (instance | witness
+        values, (num_vars, 4) Montgomery limbs; the constant 1 and public inputs already lifted with from_public).
+
+        net: .party, .n_parties, .exchange(uint8 array) -> list of every party's array in party order (a
+        broadcast).  Returns {"a": (xy, inf), "b": (xy, inf) over G2, "c": (xy, inf)}: the shares
+        MpcPairingEngine would reveal."""
+        pk, r1cs = self.pk, self.r1cs
+        leader = net.party == 0
+        z = np.ascontiguousarray(assignment, dtype=np.uint64).reshape(-1, 4)
+        if z.shape[0] != r1cs.num_vars:
+            raise ValueError("assignment has %d values, the circuit %d variables" % (z.shape[0], r1cs.num_vars))
+        n = r1cs.n
+        tx, ty, tz = triple if triple is not None else dummy_triple(n, leader)
+        zero, one = np.zeros(4, dtype=np.uint64), FR_R_LIMBS
+        r = zero if r is None else np.asarray(r, dtype=np.uint64)
+        s = zero if s is None else np.asarray(s, dtype=np.uint64)
+
+        # ---- witness map: the vectors stay on the device; only wire payloads cross PCIe for the two opens
+        ma, mb, st = H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, z, r1cs.num_inputs, r1cs.log_n, tx, ty)
+        try:
+            sx = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(ma))), n)
+            oy = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(mb))), n)
+            h_ptr = H.witness_map_finish_dev(st, tz, sx, oy, leader)
+
+            # ---- scalars of the four MSMs, resident: [assignment[1:] | 1 | 1 | r or s] (leader) and [witness | h]
+            tail_a = np.stack([one, one, r]) if leader else np.zeros((3, 4), dtype=np.uint64)
+            tail_b = np.stack([one, one, s]) if leader else np.zeros((3, 4), dtype=np.uint64)
+            m = r1cs.num_vars - 1
+            sa, sb1, sb2, slh = (p.value for p in self.streams)
+            zab = _cat(z[1:], tail_a, tail_b)               # one staging array: [assignment | tail_a | tail_b]
+            h2d = lambda dst, src, nbytes, stream: _lib.call("mpc_cuda_memcpy_h2d", C.c_void_p(dst), src.ctypes.data_as(C.c_void_p),
+                                                             C.c_size_t(nbytes), C.c_void_p(stream))
+            h2d(self.za.ptr.value, zab, (m + 3) * 32, sa)
+            h2d(self.zb.ptr.value, zab, m * 32, sb1)
+            h2d(self.zb.ptr.value + m * 32, zab[m + 3:], 3 * 32, sb1)
+            _lib.call("mpc_cuda_stream_sync", C.c_void_p(sb1))   # B2 reads zb on its own stream
+            h2d(self.lh.ptr.value, z[r1cs.num_inputs:], pk.n_l * 32, slh)
+            _lib.call("mpc_cuda_memcpy_d2d", C.c_void_p(self.lh.ptr.value + pk.n_l * 32), C.c_void_p(h_ptr),
+                      C.c_size_t(pk.n_h * 32), C.c_void_p(slh))
+            H.msm_handle_dev(pk.A, self.za, m + 3, out=self.parts[0], stream=sa)
+            H.msm_handle_dev(pk.B1, self.zb, m + 3, out=self.parts[1], stream=sb1)
+            H.msm_handle_dev(pk.B2, self.zb, m + 3, out=self.parts[2], stream=sb2)
+            H.msm_handle_dev(pk.LH, self.lh, pk.n_l + pk.n_h, out=self.parts[3], stream=slh)
+            g_a = H.sum_partials(self.parts[0], 1, stream=sa)
+            g1_b = H.sum_partials(self.parts[1], 1, stream=sb1)
+            g2_b = H.sum_partials(self.parts[2], 1, g2=True, stream=sb2)
+            lh_acc = H.sum_partials(self.parts[3], 1, stream=slh)
+        finally:
+            st.release()
+
+        # ---- g_c = s*g_a + r*g1_b - r*s*delta_g1 + l_aux_acc + h_acc   (src/groth16.rs:165-171)
+        if not r.any() and not s.any():
+            g_c = lh_acc
+        else:
+            rs = H.field_op("fr", "neg", H.field_op("fr", "mul", r[None], s[None]))[0] if leader else zero
+            pts = np.stack([g_a[0], g1_b[0], pk.delta_g1, lh_acc[0]])
+            inf = np.array([g_a[1], g1_b[1], 0, lh_acc[1]], dtype=np.uint8)
+            g_c = H.msm_g1(pts, np.stack([s, r, rs, one]), inf=inf)
+        return {"a": g_a, "b": g2_b, "c": g_c}
 
 
 def prove_party(pk, r1cs, assignment, net, triple=None, r=None, s=None):
-    """One party's share of the proof (a, b, c) from its share of the full assignment (instance | witness values,
-    (num_vars, 4) Montgomery limbs; the constant 1 and public inputs already lifted with from_public).
-
-    net: .party, .n_parties, .exchange(uint8 array) -> list of every party's array in party order (a broadcast).
-    Returns {"a": (xy, inf), "b": (xy, inf) over G2, "c": (xy, inf)}: the shares MpcPairingEngine would reveal."""
-    leader = net.party == 0
-    z = np.ascontiguousarray(assignment, dtype=np.uint64).reshape(-1, 4)
-    if z.shape[0] != r1cs.num_vars or pk.num_vars != r1cs.num_vars:
-        raise ValueError("assignment / proving key / R1CS disagree on the number of variables")
-    n = r1cs.n
-    if pk.n_h > n or pk.n_l != r1cs.num_vars - r1cs.num_inputs:
-        raise ValueError("h_query / l_query do not fit the domain / witness size")
-    tx, ty, tz = triple if triple is not None else dummy_triple(n, leader)
-    zero, one = np.zeros(4, dtype=np.uint64), FR_R_LIMBS
-    r = zero if r is None else np.asarray(r, dtype=np.uint64)
-    s = zero if s is None else np.asarray(s, dtype=np.uint64)
-
-    # ---- witness map: the vectors stay on the device; only wire payloads cross PCIe for the two opens
-    ma, mb, st = H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, z, r1cs.num_inputs, r1cs.log_n, tx, ty)
-    sx = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(ma))), n)
-    oy = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(mb))), n)
-    h_ptr = H.witness_map_finish_dev(st, tz, sx, oy, leader)
-
-    # ---- scalars of the four MSMs, resident: [assignment[1:] | 1 | 1 | r or s] (leader) and [witness | h]
-    tail_a = np.stack([one, one, r]) if leader else np.zeros((3, 4), dtype=np.uint64)
-    tail_b = np.stack([one, one, s]) if leader else np.zeros((3, 4), dtype=np.uint64)
-    m = r1cs.num_vars - 1
-    za = H.DeviceBuffer((m + 3) * 32).upload(_cat(z[1:], tail_a))
-    zb = H.DeviceBuffer((m + 3) * 32).upload(_cat(z[1:], tail_b))
-    lh = H.DeviceBuffer((pk.n_l + pk.n_h) * 32)
-    streams = _Streams(4)
+    """one-shot form of ProverSession.prove (allocates and frees the working set around one proof)"""
+    session = ProverSession(pk, r1cs)
     try:
-        sa, sb1, sb2, slh = (p.value for p in streams.ptrs)
-        _lib.call("mpc_cuda_memcpy_h2d", lh.ptr, z[r1cs.num_inputs:].ctypes.data_as(C.c_void_p), C.c_size_t(pk.n_l * 32),
-                  C.c_void_p(slh))
-        _lib.call("mpc_cuda_memcpy_d2d", C.c_void_p(lh.ptr.value + pk.n_l * 32), C.c_void_p(h_ptr), C.c_size_t(pk.n_h * 32),
-                  C.c_void_p(slh))
-        parts = [H.msm_handle_dev(pk.A, za, m + 3, stream=sa), H.msm_handle_dev(pk.B1, zb, m + 3, stream=sb1),
-                 H.msm_handle_dev(pk.B2, zb, m + 3, stream=sb2), H.msm_handle_dev(pk.LH, lh, pk.n_l + pk.n_h, stream=slh)]
-        g_a = H.sum_partials(parts[0], 1, stream=sa)
-        g1_b = H.sum_partials(parts[1], 1, stream=sb1)
-        g2_b = H.sum_partials(parts[2], 1, g2=True, stream=sb2)
-        lh_acc = H.sum_partials(parts[3], 1, stream=slh)
+        return session.prove(assignment, net, triple, r, s)
     finally:
-        streams.close()
-        st.release()
-        for b in (za, zb, lh):
-            b.free()
-    for p in parts:
-        p.free()
-
-    # ---- g_c = s*g_a + r*g1_b - r*s*delta_g1 + l_aux_acc + h_acc   (src/groth16.rs:165-171)
-    if not r.any() and not s.any():
-        g_c = lh_acc
-    else:
-        rs = H.field_op("fr", "neg", H.field_op("fr", "mul", r[None], s[None]))[0] if leader else zero
-        pts = np.stack([g_a[0], g1_b[0], pk.delta_g1, lh_acc[0]])
-        inf = np.array([g_a[1], g1_b[1], 0, lh_acc[1]], dtype=np.uint8)
-        g_c = H.msm_g1(pts, np.stack([s, r, rs, one]), inf=inf)
-    return {"a": g_a, "b": g2_b, "c": g_c}
+        session.close()
