@@ -51,6 +51,8 @@ int32_t mpc_cuda_device_count(void);
  *   "msm_window_bits"  Pippenger window width c (3..23)
  *   "msm_task_len"     maximum points one accumulation task adds (bucket splitting)
  *   "msm_host_chunks"  point-range chunks a host-buffer MSM is streamed in (copy/compute overlap), 1..16
+ *   "ntt_occupancy"    NTT pass kernels built for one more resident CTA per SM (64 registers): 0 = automatic (the
+ *                      256-row tile shape only), 1 = every shape, 2 = none
  *   "ntt_generic"      1: run every NTT pass through the generic (runtime tile shape) kernel instead of the
  *                      compile-time-shaped ones (A/B measurements; results are identical)
  *   "profile"          1: bracket pipeline stages with CUDA events on the launching stream */

@@ -17,6 +17,18 @@ using Fq2 = Fp2<consts::FqParams>;
 template <class P> static Fp<P> sqr_wide_of(const Fp<P>& x) { return sqr_wide(x); }
 template <class P> static Fp2<P> sqr_wide_of(const Fp2<P>& x) { return sqr(x); }
 
+// the NTT's lazily reduced butterfly arithmetic against the strict one: operands lifted to [p, 2p), then
+// (x - y) * y and x + y through add_lazy / sub_lazy / mul_lazy, brought back with reduce_full; must equal
+// mul(sub(x, y), y) + add(x, y) computed strictly
+template <class P> static Fp<P> lazy_chain(const Fp<P>& x, const Fp<P>& y) {
+    Fp<P> xl = add_lazy(x, Fp<P>::modulus()), yl = add_lazy(y, Fp<P>::modulus());      // x + p, y + p (< 2p)
+    Fp<P> prod = mul_lazy(sub_lazy(xl, yl), y);                                        // < 2p
+    Fp<P> sum = add_lazy(xl, yl);                                                      // < 2p
+    Fp<P> both = add_lazy(prod, sum);
+    return reduce_full(both);
+}
+template <class P> static Fp2<P> lazy_chain(const Fp2<P>& x, const Fp2<P>&) { return x; }
+
 template <class F>
 static void vec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
     constexpr int N = F::N;
@@ -34,6 +46,7 @@ static void vec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, 
             case 10: r = sqr_wide_of(x); break;
             case 9: r = dbl(x); break;
             case 11: r = inv_euclid(x); break;
+            case 12: r = lazy_chain(x, y); break;
             default: r = x; break;
         }
         memcpy(out + N * i, &r, 4 * N);

@@ -199,3 +199,11 @@ def test_emulated_jacobian_doubling_chain(emu, orc, group):
         out = np.zeros(limbs, dtype=np.uint64)
         fn(_p32(base), C.c_uint32(k), _p32(out))
         assert from_arr(out) == P.ec_mul(F, 1 << k, from_arr(base))
+
+
+def test_emulated_lazy_reduction(emu, orc, pkg):
+    """add_lazy / sub_lazy / mul_lazy / reduce_full (values in [0, 2p), the NTT butterflies) agree with the strict
+    arithmetic, including the extreme operands"""
+    a, b = _edge_fr(pkg, 400, 31), _edge_fr(pkg, 400, 32)[::-1].copy()
+    exp = orc.fr("add", orc.fr("mul", orc.fr("sub", a, b), b), orc.fr("add", a, b))
+    assert np.array_equal(_vec(emu, "emu_fr_vec", 12, a, b), exp)

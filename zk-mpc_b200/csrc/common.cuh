@@ -99,6 +99,7 @@ extern std::atomic<int64_t> g_opt_msm_task_len;
 extern std::atomic<int64_t> g_opt_msm_host_chunks;
 extern std::atomic<int64_t> g_opt_profile;
 extern std::atomic<int64_t> g_opt_ntt_generic;
+extern std::atomic<int64_t> g_opt_ntt_occupancy;
 
 inline cudaStream_t pick_stream(void* user, cudaStream_t mine) { return user ? (cudaStream_t)user : mine; }
 

@@ -498,3 +498,94 @@ HD Fp<P> inv_euclid(const Fp<P>& a) {
     }
     return is_one<N>(u.v) ? b : c;
 }
+
+// ---- lazy reduction for the NTT butterflies --------------------------------------------------------------
+// Values are kept in [0, 2p) between butterflies instead of [0, p): p has at least 3 spare bits in its top limb,
+// so 4p fits the limbs.  u + v is brought back below 2p with one conditional subtraction of 2p; u - v is
+// computed as u - v + 2p in (0, 4p) and only ever feeds a Montgomery product with a fully reduced twiddle,
+// whose result a * w / R + p * (m / R) < 4p * p / R + p < 2p needs no final subtraction at all (p / R < 1/8).
+// reduce_full brings a value from [0, 4p) to the canonical [0, p) where the transform ends.
+namespace fp_detail {
+template <class P> HD uint32_t mod2(int i) {      // limb i of 2p
+    return (P::mod(i) << 1) | (i ? (P::mod(i - 1) >> 31) : 0u);
+}
+// r = (r >= m) ? r - m : r for m = 2p
+template <class P>
+HD void cond_sub_2p(uint32_t* r) {
+    constexpr int N = P::N;
+    uint32_t t[N];
+    t[0] = ptx::sub_cc(r[0], mod2<P>(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(r[i], mod2<P>(i));
+    uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
+}
+}  // namespace fp_detail
+
+// a, b in [0, 2p) -> a + b in [0, 2p)
+template <class P>
+HD Fp<P> add_lazy(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    r.v[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);
+    fp_detail::cond_sub_2p<P>(r.v);
+    return r;
+}
+
+// a, b in [0, 2p) -> a - b + 2p in (0, 4p): input of mul_lazy only
+template <class P>
+HD Fp<P> sub_lazy(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    r.v[N - 1] = ptx::subc(a.v[N - 1], b.v[N - 1]);
+    r.v[0] = ptx::add_cc(r.v[0], fp_detail::mod2<P>(0));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(r.v[i], fp_detail::mod2<P>(i));
+    r.v[N - 1] = ptx::addc(r.v[N - 1], fp_detail::mod2<P>(N - 1));
+    return r;
+}
+
+// Montgomery product of a in [0, 4p) with b in [0, p), without the final subtraction: result in [0, 2p)
+template <class P>
+HD Fp<P> mul_lazy(const Fp<P>& a, const Fp<P>& b) {
+    using namespace fp_detail;
+    constexpr int N = P::N, H = N / 2;
+    uint64_t ev[H], od[H];
+    wmul_row_first<N>(ev, od, a.v, b.v[0]);
+    wredc_row<P>(ev, od);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        wmul_row<N>(od, ev, a.v, b.v[i]);
+        wredc_row<P>(od, ev);
+        if (i + 1 < N) {
+            wmul_row<N>(ev, od, a.v, b.v[i + 1]);
+            wredc_row<P>(ev, od);
+        }
+    }
+    Fp<P> r;
+    r.v[0] = ptx::add_cc(lo32(ev[0]), hi32(od[0]));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) {
+        uint32_t e = (i & 1) ? hi32(ev[i / 2]) : lo32(ev[i / 2]);
+        uint32_t o = ((i + 1) & 1) ? hi32(od[(i + 1) / 2]) : lo32(od[(i + 1) / 2]);
+        r.v[i] = ptx::addc_cc(e, o);
+    }
+    r.v[N - 1] = ptx::addc(hi32(ev[H - 1]), 0);
+    return r;
+}
+
+// [0, 4p) -> [0, p)
+template <class P>
+HD Fp<P> reduce_full(const Fp<P>& a) {
+    Fp<P> r = a;
+    fp_detail::cond_sub_2p<P>(r.v);
+    fp_detail::final_sub<P>(r.v);
+    return r;
+}

@@ -23,6 +23,7 @@
 using namespace mpc;
 
 namespace mpc {
+std::atomic<int64_t> g_opt_ntt_occupancy{0};    // 1: the pass kernels compiled for one more CTA per SM
 std::atomic<int64_t> g_opt_ntt_generic{0};      // 1: always run the generic pass kernel (A/B measurements, tests)
 }
 
@@ -124,6 +125,28 @@ DEV void bfly(Fr& u, Fr& v, const Fr* __restrict__ tw, uint32_t k, uint32_t l, b
     v = l > 1 ? mul(d, load_fe_ro(tw + k)) : d;       // l == 1: the only twiddle is 1
 }
 
+// The same butterfly on lazily reduced values (fp.cuh: everything in the tile stays in [0, 2p); one conditional
+// subtraction per addition, none per product): the pass kernel's version.  INV is a compile-time flag so the
+// forward kernels carry no operand selects.
+template <bool INV>
+DEV void bfly_lazy(Fr& u, Fr& v, const Fr* __restrict__ tw, uint32_t k, uint32_t l) {
+    Fr d;
+    if (INV) {
+        const bool swap = k != 0;
+        if (swap) k = (1u << (l - 1)) - k;
+        d = swap ? sub_lazy(v, u) : sub_lazy(u, v);
+    } else {
+        d = sub_lazy(u, v);
+    }
+    u = add_lazy(u, v);
+    if (l > 1) {
+        v = mul_lazy(d, load_fe_ro(tw + k));
+    } else {                                          // l == 1: the only twiddle is 1
+        fp_detail::cond_sub_2p<consts::FrParams>(d.v);
+        v = d;
+    }
+}
+
 // Every thread owns four rows of the tile and runs TWO stages on them in registers between
 // shared-memory exchanges (radix-4 step = 4 products, half the shared traffic and barriers of radix-2);
 // an odd stage count ends with one radix-2 stage.
@@ -131,8 +154,10 @@ DEV void bfly(Fr& u, Fr& v, const Fr* __restrict__ tw, uint32_t k, uint32_t l, b
 // elements) is a compile-time constant, so the rounds unroll and the index algebra folds into immediates;
 // DEG = 0 is the generic kernel for the small shapes.
 constexpr int NTT_THREADS = 256;
-template <int DEG, int LAST>
-__global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS, DEG == 8 ? 3 : DEG == 7 ? 6 : DEG == 6 ? 12 : 3)
+// OCC = 1: compiled for one more resident CTA per SM (64 registers instead of 80)
+template <int DEG, int LAST, bool INV, int OCC>
+__global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS,
+                                  (DEG == 8 ? 3 : DEG == 7 ? 6 : DEG == 6 ? 12 : 3) + (OCC ? (DEG == 8 ? 1 : DEG == 7 ? 2 : DEG == 6 ? 4 : 1) : 0))
     k_ntt_pass(PassArgs a) {
     extern __shared__ uint32_t sm[];
     const uint32_t t = threadIdx.x;
@@ -145,7 +170,6 @@ __global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS, DEG == 8 ? 3 :
     const uint32_t tile = blockIdx.x;
     const Fr* src = a.src + (size_t)blockIdx.y * n;
     Fr* dst = a.dst + (size_t)blockIdx.y * n;
-    const bool inverse = a.inverse != 0;
 
     // tile origin: non-last: i = origin + j*T + c;  last: i = (hb + (bitrev(c) << (s0-lc))) * rows + j
     uint32_t origin = 0, lo0 = 0, hb = 0;
@@ -188,10 +212,10 @@ __global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS, DEG == 8 ? 3 :
             Fr x0 = sm_load(sm, E, p0), x1 = sm_load(sm, E, p0 ^ s1), x2 = sm_load(sm, E, p0 ^ s2),
                x3 = sm_load(sm, E, p0 ^ s3);
             const uint32_t k = (qq << log_t) + lo;
-            bfly(x0, x2, a.tw[r], k, l0, inverse);
-            bfly(x1, x3, a.tw[r], k + (h << log_t), l0, inverse);
-            bfly(x0, x1, a.tw[r + 1], k, l0 - 1, inverse);
-            bfly(x2, x3, a.tw[r + 1], k, l0 - 1, inverse);
+            bfly_lazy<INV>(x0, x2, a.tw[r], k, l0);
+            bfly_lazy<INV>(x1, x3, a.tw[r], k + (h << log_t), l0);
+            bfly_lazy<INV>(x0, x1, a.tw[r + 1], k, l0 - 1);
+            bfly_lazy<INV>(x2, x3, a.tw[r + 1], k, l0 - 1);
             sm_store(sm, E, p0, x0);
             sm_store(sm, E, p0 ^ s1, x1);
             sm_store(sm, E, p0 ^ s2, x2);
@@ -207,7 +231,7 @@ __global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS, DEG == 8 ? 3 :
             const uint32_t lo = last ? 0 : lo0 + c;
             const uint32_t p0 = swz(((2 * bq) << lc) + c), p1 = p0 ^ swz(C);
             Fr x0 = sm_load(sm, E, p0), x1 = sm_load(sm, E, p1);
-            bfly(x0, x1, a.tw[r], lo, l0, inverse);
+            bfly_lazy<INV>(x0, x1, a.tw[r], lo, l0);
             sm_store(sm, E, p0, x0);
             sm_store(sm, E, p1, x1);
         }
@@ -223,7 +247,9 @@ __global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS, DEG == 8 ? 3 :
             // row j of the store is destination block j: source row bitrev(j)
             Fr x = sm_load(sm, E, swz((bitrev(j, deg) << lc) + cc));
             uint32_t d = (j << a.s0) + (tile << lc) + cc;
+            // back to the canonical range: a strict product does it (input < 2p), else two conditional subtractions
             if (a.scale) x = mul(x, load_fe_ro(a.scale));
+            else x = reduce_full(x);
             if (a.post_lo) {
                 x = mul(x, load_fe_ro(a.post_lo + (d & ((1u << COSET_LO_BITS) - 1))));
                 if (a.log_n > COSET_LO_BITS) x = mul(x, load_fe_ro(a.post_hi + (d >> COSET_LO_BITS)));
@@ -233,19 +259,31 @@ __global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS, DEG == 8 ? 3 :
     }
 }
 
-template <int DEG, int LAST>
-int32_t launch_pass(const PassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s) {
+template <int DEG, int LAST, bool INV, int OCC>
+int32_t launch_pass_occ(const PassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s) {
     static bool configured[64] = {};                 // per device of the init list; benign race (idempotent call)
     int dev = current_device_index();
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         // 16-32 KB tiles: let several CTAs share an SM (the default carveout fits one)
-        MPC_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<DEG, LAST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        MPC_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<DEG, LAST, INV, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           cudaSharedmemCarveoutMaxShared));
         configured[dev] = true;
     }
-    k_ntt_pass<DEG, LAST><<<grid, threads, smem, s>>>(a);
+    k_ntt_pass<DEG, LAST, INV, OCC><<<grid, threads, smem, s>>>(a);
     MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
+}
+template <int DEG, int LAST>
+int32_t launch_pass(const PassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s) {
+    // measured on B200 (tools/time_ntt.py): the 64-register build wins for the 2^8-row tiles (4 CTAs of 256 threads
+    // per SM instead of 3: 3.52 -> 3.34 ms at 2^24) and loses for the smaller ones; option ntt_occupancy: 1 = all
+    // shapes, 2 = none
+    const int64_t occ = g_opt_ntt_occupancy.load(std::memory_order_relaxed);
+    if (DEG && (occ == 1 || (occ == 0 && DEG == 8)))
+        return a.inverse ? launch_pass_occ<DEG, LAST, true, DEG ? 1 : 0>(a, grid, threads, smem, s)
+                         : launch_pass_occ<DEG, LAST, false, DEG ? 1 : 0>(a, grid, threads, smem, s);
+    return a.inverse ? launch_pass_occ<DEG, LAST, true, 0>(a, grid, threads, smem, s)
+                     : launch_pass_occ<DEG, LAST, false, 0>(a, grid, threads, smem, s);
 }
 
 // n == 1: ifft / coset_ifft multiply by 1⁻¹ = 1, everything is the identity
