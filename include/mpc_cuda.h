@@ -50,6 +50,8 @@ int32_t mpc_cuda_device_count(void);
 /* Tuning knobs for benchmarks and tests (process-wide atomics; 0 restores the automatic choice):
  *   "msm_window_bits"  Pippenger window width c (3..23)
  *   "msm_task_len"     maximum points one accumulation task adds (bucket splitting)
+ *   "msm_affine"       batched-affine pre-reduction of the bucket lists before the XYZZ accumulation: 0 = automatic
+ *                      (two rounds when buckets hold >= 8 entries on average), 1 = off, 2 = one round, 3 = two rounds
  *   "msm_host_chunks"  point-range chunks a host-buffer MSM is streamed in (copy/compute overlap), 1..16
  *   "ntt_occupancy"    NTT pass kernels built for one more resident CTA per SM (64 registers): 0 = automatic (the
  *                      256-row tile shape only), 1 = every shape, 2 = none

@@ -25,7 +25,7 @@ def H(pkg):
 @pytest.fixture(autouse=True)
 def _reset_options(H):
     yield
-    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks"):
+    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks", "msm_affine"):
         H.set_option(name, 0)
 
 
@@ -335,3 +335,81 @@ def test_sharded_ntt_and_msm_on_real_devices(H, orc, pkg, bases8k, log_g):
     sc = pkg.synth.fr_uniform(0xF30, 8192)
     assert _same(H.msm_handle(h, sc), orc.g1_msm(bases8k, sc, threads=8))
     h.release()
+
+
+# ----------------------------------------------------------------------------- batched-affine pre-reduction
+@pytest.mark.parametrize("rounds_opt", [2, 3])          # option msm_affine: 2 = one round, 3 = two rounds
+def test_g1_affine_prereduction_matches_oracle(H, orc, pkg, bases8k, rounds_opt):
+    """k_affine_pairs (pairwise affine additions with one shared inversion per warp) in front of the XYZZ
+    accumulation: forced on for small inputs, every window width class, duplicates (tangent), P + (-P) (infinity),
+    infinity bases, skewed scalars (one huge bucket), table mode, chunked streaming"""
+    H.set_option("msm_affine", rounds_opt)
+    try:
+        n = 8000
+        for seed, sc in ((1, pkg.synth.fr_uniform(0x3A0, n)), (2, pkg.synth.fr_witness_like(0x3B0, n))):
+            assert _same(H.msm_g1(bases8k[:n], sc), orc.g1_msm(bases8k[:n], sc, threads=8)), seed
+        for c in (4, 9, 13):
+            H.set_option("msm_window_bits", c)
+            sc = pkg.synth.fr_uniform(0x3C0 + c, 3000)
+            assert _same(H.msm_g1(bases8k[:3000], sc), orc.g1_msm(bases8k[:3000], sc, threads=8)), c
+        H.set_option("msm_window_bits", 0)
+        # the same point many times with the same scalar (tangent case in every pair), P and -P, infinity bases
+        bases, scalars = bases8k[:64].copy(), pkg.synth.fr_uniform(0x3D0, 64)
+        bases[1:9] = bases[0]
+        scalars[1:9] = scalars[0]
+        q = P.g1_from_arr(bases[20])
+        bases[21] = P.g1_to_arr((q[0], (-q[1]) % P.Q_MOD))[0]
+        scalars[21] = scalars[20]
+        infs = np.zeros(64, dtype=np.uint8)
+        infs[[5, 40]] = 1
+        assert _same(H.msm_g1(bases, scalars, inf=infs), orc.g1_msm(bases, scalars, inf=infs))
+        same_b, same_s = np.tile(bases[7], (57, 1)), np.tile(scalars[7], (57, 1))
+        assert _same(H.msm_g1(same_b, same_s), orc.g1_msm(same_b, same_s))
+        assert H.msm_g1(bases[20:22], scalars[20:22])[1] == 1
+        ones = np.tile(pkg.synth.FR_R_LIMBS, (n, 1))
+        H.set_option("msm_task_len", 5)
+        assert _same(H.msm_g1(bases8k[:n], ones), orc.g1_msm(bases8k[:n], ones, threads=8))
+        H.set_option("msm_task_len", 0)
+        # table mode and chunked streaming (later chunks merge into the buckets of the earlier ones)
+        h = H.register_bases(bases8k).precompute(9)
+        sc = pkg.synth.fr_uniform(0x3E0, 8192)
+        assert _same(H.msm_handle(h, sc), orc.g1_msm(bases8k, sc, threads=8))
+        h.release()
+        H.set_option("msm_host_chunks", 3)
+        assert _same(H.msm_g1(bases8k[:n], sc[:n]), orc.g1_msm(bases8k[:n], sc[:n], threads=8))
+    finally:
+        H.set_option("msm_affine", 0)
+
+
+def test_g2_affine_prereduction_matches_oracle(H, orc, pkg):
+    g, _ = P.g2_to_arr((P.G2_X, P.G2_Y))
+    bases = orc.g2_generate(g, 0xB4, 500)
+    bases[1:5] = bases[0]
+    H.set_option("msm_affine", 3)
+    try:
+        for sc in (pkg.synth.fr_uniform(0x3F0, 500), pkg.synth.fr_witness_like(0x3F1, 500)):
+            sc[1:5] = sc[0]
+            assert _same(H.msm_g2(bases, sc), orc.g2_msm(bases, sc, threads=8))
+    finally:
+        H.set_option("msm_affine", 0)
+
+
+def test_g1_affine_prereduction_full_size_exact(H, orc, pkg):
+    """2^20 points, where the automatic rule turns the pre-reduction on (plain and table mode)"""
+    log_n = 20
+    n = 1 << log_n
+    seed = pkg.synth.bench_seed(log_n) + 0x300
+    dev = H.g1_generate(seed, n)
+    h = H.register_bases_dev(dev, n)
+    ks = helpers.gen_ks(pkg, seed, n)
+    sc = pkg.synth.fr_uniform(seed, n)
+    exp = helpers.expected_msm_of_generated(orc, sc, ks)
+    assert _same(H.msm_handle(h, sc), exp)
+    H.set_option("msm_affine", 1)
+    assert _same(H.msm_handle(h, sc), exp)                 # and the same without it
+    H.set_option("msm_affine", 0)
+    h.precompute(0)
+    assert _same(H.msm_handle(h, sc), exp)
+    wl = pkg.synth.fr_witness_like(seed + 1, n)
+    assert _same(H.msm_handle(h, wl), helpers.expected_msm_of_generated(orc, wl, ks))
+    h.release(); dev.free()

@@ -97,6 +97,7 @@ struct ProfileScope {
 extern std::atomic<int64_t> g_opt_msm_window_bits;
 extern std::atomic<int64_t> g_opt_msm_task_len;
 extern std::atomic<int64_t> g_opt_msm_host_chunks;
+extern std::atomic<int64_t> g_opt_msm_affine;
 extern std::atomic<int64_t> g_opt_profile;
 extern std::atomic<int64_t> g_opt_ntt_generic;
 extern std::atomic<int64_t> g_opt_ntt_occupancy;

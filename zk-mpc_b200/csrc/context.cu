@@ -284,6 +284,9 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value) {
         g_opt_ntt_occupancy = value;
     } else if (!strcmp(name, "ntt_generic")) {
         g_opt_ntt_generic = value ? 1 : 0;
+    } else if (!strcmp(name, "msm_affine")) {
+        MPC_ARG_CHECK(value >= 0 && value <= 3);
+        g_opt_msm_affine = value;
     } else if (!strcmp(name, "msm_host_chunks")) {
         MPC_ARG_CHECK(value >= 0 && value <= 16);
         g_opt_msm_host_chunks = value;

@@ -215,6 +215,35 @@ DEV Fp2<P> warp_bcast(const Fp2<P>& a, int src) {
     return r;
 }
 
+template <class P>
+DEV Fp<P> warp_shfl_up(const Fp<P>& a, int delta) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], delta);
+    return r;
+}
+template <class P>
+DEV Fp2<P> warp_shfl_up(const Fp2<P>& a, int delta) {
+    Fp2<P> r;
+    r.c0 = warp_shfl_up(a.c0, delta);
+    r.c1 = warp_shfl_up(a.c1, delta);
+    return r;
+}
+template <class P>
+DEV Fp<P> warp_shfl_down(const Fp<P>& a, int delta) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], delta);
+    return r;
+}
+template <class P>
+DEV Fp2<P> warp_shfl_down(const Fp2<P>& a, int delta) {
+    Fp2<P> r;
+    r.c0 = warp_shfl_down(a.c0, delta);
+    r.c1 = warp_shfl_down(a.c1, delta);
+    return r;
+}
+
 // r[j] = a[j] * b[j] for j < K (K <= 4), product j computed by lane j, every lane receives all results
 template <int K, class F>
 DEV void warp_mul(F* r, const F* a, const F* b) {

@@ -89,6 +89,8 @@ struct Plan {
     uint32_t scan_blocks;        // blocks of the task scan (SCAN_ITEMS buckets each)
     uint32_t red_m, red_t;       // bucket-reduce: red_t chunks of red_m buckets per window
     uint32_t sum_parts;          // window-sum: first-level blocks per window
+    uint32_t aff;                // affine pre-reduction rounds (0 or 2): bucket runs padded to 2^aff entries
+    size_t snp;                  // slots per window of the sorted list (= sn_cap when aff == 0)
 };
 
 constexpr uint32_t HI_BITS_MAX = 11;            // <= 2048 write streams per CTA in the level-1 scatter
@@ -127,10 +129,25 @@ inline Plan make_plan(size_t n, size_t cap, int sm_count, uint32_t table_c) {
     size_t by_len = (p.sn_cap + 8191) / 8192;
     p.chunks = (uint32_t)(by_len < want ? by_len : want);
     if (p.chunks < 1) p.chunks = 1;
+    // Affine pre-reduction: measured on B200 (tools/affine_ab.py, profiles/r2_affine_ab.jsonl) two rounds win from
+    // ~2^27 sorted entries (2^24 points: 108.5 -> 96.3 ms plain, 90.8 -> 82.8 ms with the table), one round between
+    // 2^25.5 and 2^27 (2^22 points: 34.0 -> 31.7 ms), none below (the shared inversions stop amortising); the
+    // padding of every run to 2^aff entries also needs buckets of >= 8 entries on average.
+    size_t nbuckets_all = (size_t)p.snwin * p.nb, entries_all = cap * (size_t)p.nwin;
+    int64_t aff_opt = g_opt_msm_affine.load(std::memory_order_relaxed);
+    p.aff = 0;
+    if (aff_opt == 0 && entries_all >= 8 * nbuckets_all)
+        p.aff = entries_all >= ((size_t)3 << 25) ? 2 : entries_all >= ((size_t)3 << 24) ? 1 : 0;
+    else if (aff_opt >= 2) p.aff = (uint32_t)(aff_opt - 1);              // 2 -> one round, 3 -> two rounds
+    p.snp = p.sn_cap;
+    if (p.aff) {
+        size_t padm = ((size_t)1 << p.aff) - 1, hb = (size_t)1 << p.hi_bits, lb = (size_t)1 << p.lo_bits;
+        p.snp = (p.sn_cap + hb * (padm * lb + padm + 1) + padm + padm) & ~padm;
+    }
     int64_t tl = g_opt_msm_task_len.load(std::memory_order_relaxed);
     if (tl <= 0) {
         // enough tasks to balance the resident threads, but not so short that joins dominate
-        size_t entries = cap * (size_t)p.nwin;
+        size_t entries = (cap * (size_t)p.nwin) >> p.aff;
         size_t resident = (size_t)sm_count * 384;
         tl = (int64_t)(entries / (resident * 8));
         if (tl < 32) tl = 32;
@@ -267,11 +284,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter1(const uint32_t* __res
 constexpr int SORT2_THREADS = 1024;
 constexpr int SORT2_ILP = 4;
 
+// pad_log > 0 (affine pre-reduction, below): every bucket's run starts at a multiple of 2^pad_log in the output
+// list and is padded to such a multiple with holes (the list is pre-filled with 0xffffffff); the window's list
+// then has `out_stride` slots, and bucket_start / bucket_size are written in units of 2^pad_log entries, i.e. as
+// positions in the array of pre-reduced points.
 __global__ void __launch_bounds__(SORT2_THREADS) k_sort2(const uint2* __restrict__ pairs,
                                                          const uint32_t* __restrict__ part_start, size_t n,
                                                          uint32_t lo_bits, uint32_t hbins, uint32_t* __restrict__ sorted,
                                                          uint32_t* __restrict__ bucket_start,
-                                                         uint32_t* __restrict__ bucket_size) {
+                                                         uint32_t* __restrict__ bucket_size, uint32_t pad_log,
+                                                         size_t out_stride) {
     extern __shared__ uint32_t sm[];            // lbins counters, then blockDim.x scan slots
     const uint32_t lbins = 1u << lo_bits;
     uint32_t* cnt = sm;
@@ -300,22 +322,26 @@ __global__ void __launch_bounds__(SORT2_THREADS) k_sort2(const uint2* __restrict
     uint32_t per = (lbins + blockDim.x - 1) / blockDim.x;
     uint32_t b0 = threadIdx.x * per, b1 = b0 + per < lbins ? b0 + per : lbins;
     if (b0 > lbins) b0 = lbins;
+    const uint32_t padm = (1u << pad_log) - 1u;
     uint32_t tot = 0;
-    for (uint32_t b = b0; b < b1; b++) tot += cnt[b];
-    uint32_t run = lo + block_exclusive_scan(tot, scan, nullptr);
+    for (uint32_t b = b0; b < b1; b++) tot += (cnt[b] + padm) & ~padm;
+    // the partition's output region: exact lists start where the input run starts; padded lists leave room for
+    // the worst-case padding of every earlier partition of the window
+    uint32_t obase = pad_log ? ((lo + p * (padm * lbins + padm + 1u) + padm) & ~padm) : lo;
+    uint32_t run = obase + block_exclusive_scan(tot, scan, nullptr);
     // bucket id = (bin << hi_bits) | partition: level 1 splits on the LOW bits of the bucket id, which
     // stay well spread when the digits are skewed towards small values (top window, small scalars)
     const uint32_t hi_bits = 31 - __clz(hbins);
     size_t g0 = ((size_t)w << (lo_bits + hi_bits)) + p;
     for (uint32_t b = b0; b < b1; b++) {
-        uint32_t t = cnt[b];
-        bucket_start[g0 + ((size_t)b << hi_bits)] = run;
-        bucket_size[g0 + ((size_t)b << hi_bits)] = t;
+        uint32_t t = cnt[b], tp = (t + padm) & ~padm;
+        bucket_start[g0 + ((size_t)b << hi_bits)] = run >> pad_log;
+        bucket_size[g0 + ((size_t)b << hi_bits)] = tp >> pad_log;
         cnt[b] = run;
-        run += t;
+        run += tp;
     }
     __syncthreads();
-    uint32_t* out = sorted + (size_t)w * n;
+    uint32_t* out = sorted + (size_t)w * out_stride;
     for (uint32_t i0 = lo; i0 < hi; i0 += step) {
         uint2 e[SORT2_ILP];
 #pragma unroll
@@ -406,7 +432,9 @@ __global__ void __launch_bounds__(1024) k_build_tasks(const uint32_t* __restrict
 // lanes of a warp stay converged on the mixed addition whatever the task lengths are.
 // merge != 0 (second and later chunks of a streamed MSM): a bucket's accumulator starts from the value the
 // earlier chunks left in it instead of infinity — no extra field products.
-template <class F>
+// DENSE: the tasks run over an array of pre-reduced affine points (k_affine_pairs) instead of an index list into
+// the bases: sequential 96-byte reads, entries (0, 0) are holes.
+template <class F, bool DENSE>
 __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(const Affine<F>* __restrict__ bases,
                                                             const uint32_t* __restrict__ sorted, size_t n, uint32_t nb,
                                                             const uint4* __restrict__ tasks,
@@ -417,7 +445,7 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(cons
     XYZZ<F> acc = XYZZ<F>::infinity();
     uint32_t k = 0, len = 0, task_id = 0;
     uint4 t = make_uint4(0, 0, 0, 0);
-    const uint32_t* list = sorted;
+    size_t first = 0;                     // slot of the task's first entry in the window-major list / point array
     while (true) {
         if (k == len) {
             if (len) store_pod(t.w ? buckets + t.z : partials + task_id, acc);
@@ -426,15 +454,133 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(cons
             t = __ldg(tasks + task_id);
             k = 0;
             len = t.y;
-            list = sorted + (size_t)(t.z / nb) * n + t.x;
+            first = (size_t)(t.z / nb) * n + t.x;
             if (merge && t.w) acc = load_pod(buckets + t.z);
             else acc = XYZZ<F>::infinity();
         }
-        uint32_t e = __ldg(list + k);
-        k++;
-        Affine<F> p = load_pod_ro(bases + (e & ~msm::DIGIT_NEG));
-        if (e & msm::DIGIT_NEG) p.y = neg(p.y);
-        xyzz_madd(acc, p.x, p.y);
+        if (DENSE) {
+            Affine<F> p = load_pod_ro(bases + first + k);
+            k++;
+            if (p.x.is_zero() && p.y.is_zero()) continue;
+            xyzz_madd(acc, p.x, p.y);
+        } else {
+            uint32_t e = __ldg(sorted + first + k);
+            k++;
+            Affine<F> p = load_pod_ro(bases + (e & ~msm::DIGIT_NEG));
+            if (e & msm::DIGIT_NEG) p.y = neg(p.y);
+            xyzz_madd(acc, p.x, p.y);
+        }
+    }
+}
+
+// ---- affine pre-reduction --------------------------------------------------------------------------------
+// Bucket accumulation sits on the IMAD.WIDE pipe at ~0.85 of its ceiling, so the only way to make it faster is
+// fewer field products per point.  A mixed XYZZ addition costs 10; an affine chord addition costs 3 once the
+// inverse of x1 - x0 is known, and Montgomery's trick (ff/src/fields/mod.rs:597-660) turns one inversion into 3
+// products per element of a batch.  The sorted lists are laid out with every bucket's run padded to a multiple
+// of 4 (k_sort2, pad_log = 2), so two rounds of *pairwise* affine additions over plain position arithmetic —
+// entries (2i, 2i+1) never straddle a bucket — shrink every bucket's list 4x before the XYZZ accumulation:
+// 3.5 + 1.75 + 2.5 = 7.75 products per original entry instead of 10.
+// One lane handles AFF_B pairs per batch (prefix products in local memory), the 32 lanes of a warp share ONE
+// inversion through a shuffle product scan, and that inversion is the binary-Euclid one: shifts and adds on the
+// ALU pipe, overlapping the other warps' multiplier work.  (0, 0) is not on the curve and encodes "no point"
+// (hole or P + (-P)); P + P takes the tangent.  The group element of every bucket is unchanged.
+#ifndef MSM_AFF_B
+#define MSM_AFF_B 256
+#endif
+constexpr int AFF_B = MSM_AFF_B;   // pairs per lane per shared inversion (prefix products: AFF_B field elements of local memory)
+constexpr int AFF_THREADS = 128;
+
+template <class F>
+DEV bool aff_none(const Affine<F>& p) { return p.x.is_zero() && p.y.is_zero(); }
+
+// kind: 0 nothing, 1 first only, 2 second only, 3 chord, 4 tangent; d = the denominator to invert (1 if none)
+template <class F, bool GATHER>
+DEV int aff_load_pair(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, size_t i, size_t npairs,
+                      Affine<F>& a, Affine<F>& b, F& d) {
+    d = F::one();
+    if (i >= npairs) return 0;
+    bool va, vb;
+    if (GATHER) {
+        uint2 e = __ldg(reinterpret_cast<const uint2*>(idx) + i);
+        va = e.x != 0xffffffffu;
+        vb = e.y != 0xffffffffu;
+        if (va) {
+            a = load_pod_ro(pts + (e.x & ~msm::DIGIT_NEG));
+            if (e.x & msm::DIGIT_NEG) a.y = neg(a.y);
+        }
+        if (vb) {
+            b = load_pod_ro(pts + (e.y & ~msm::DIGIT_NEG));
+            if (e.y & msm::DIGIT_NEG) b.y = neg(b.y);
+        }
+    } else {
+        a = load_pod_ro(pts + 2 * i);
+        b = load_pod_ro(pts + 2 * i + 1);
+        va = !aff_none(a);
+        vb = !aff_none(b);
+    }
+    if (!va) return vb ? 2 : 0;
+    if (!vb) return 1;
+    F dx = sub(b.x, a.x);
+    if (!dx.is_zero()) { d = dx; return 3; }
+    if (a.y == b.y && !a.y.is_zero()) { d = dbl(a.y); return 4; }
+    return 0;                                   // P + (-P) (or a 2-torsion point doubled): the point at infinity
+}
+
+// `batch` (<= AFF_B) pairs per lane share one inversion: long batches amortise it, short ones keep every warp of
+// the machine busy on small inputs (chosen by the host from the pair count)
+template <class F, bool GATHER>
+__global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* __restrict__ pts,
+                                                              const uint32_t* __restrict__ idx, size_t npairs,
+                                                              Affine<F>* __restrict__ out, int batch) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    F pre[AFF_B];                               // exclusive prefix products of this lane's denominators
+    for (size_t base = warp * (32 * (size_t)batch); base < npairs; base += nwarps * (32 * (size_t)batch)) {
+        F run = F::one();
+        for (int k = 0; k < batch; k++) {
+            Affine<F> a, b;
+            F d;
+            aff_load_pair<F, GATHER>(pts, idx, base + (size_t)k * 32 + lane, npairs, a, b, d);
+            pre[k] = run;
+            run = mul(run, d);
+        }
+        // 1 / (this lane's product) from ONE inversion per warp: inclusive prefix and suffix product scans
+        F pfx = run, sfx = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            F up = warp_shfl_up(pfx, off), dn = warp_shfl_down(sfx, off);
+            if (lane >= (uint32_t)off) pfx = mul(pfx, up);
+            if (lane + off < 32) sfx = mul(sfx, dn);
+        }
+        F total = warp_bcast(pfx, 31);
+        F before = warp_shfl_up(pfx, 1), after = warp_shfl_down(sfx, 1);
+        F inv_run = inv_euclid(total);          // same data on every lane: no divergence
+        if (lane > 0) inv_run = mul(inv_run, before);
+        if (lane < 31) inv_run = mul(inv_run, after);
+        for (int k = batch - 1; k >= 0; k--) {
+            const size_t i = base + (size_t)k * 32 + lane;
+            Affine<F> a, b, r;
+            F d;
+            int kind = aff_load_pair<F, GATHER>(pts, idx, i, npairs, a, b, d);
+            F dinv = mul(inv_run, pre[k]);
+            inv_run = mul(inv_run, d);
+            if (kind >= 3) {
+                F lam = kind == 3 ? mul(sub(b.y, a.y), dinv) : mul(add(dbl(sqr(a.x)), sqr(a.x)), dinv);
+                F x3 = sub(sub(sqr(lam), a.x), kind == 3 ? b.x : a.x);
+                r.y = sub(mul(lam, sub(a.x, x3)), a.y);
+                r.x = x3;
+            } else if (kind == 1) {
+                r = a;
+            } else if (kind == 2) {
+                r = b;
+            } else {
+                r.x = F::zero();
+                r.y = F::zero();
+            }
+            if (i < npairs) store_pod(out + i, r);
+        }
     }
 }
 
@@ -668,8 +814,10 @@ struct MsmJob {
     uint2* pairs;
     uint4* tasks;
     XYZZ<F>*buckets, *partials, *chunk_res, *wpart, *wsum;
+    Scratch s_q1, s_q2;
+    Affine<F>*q1 = nullptr, *q2 = nullptr;       // affine pre-reduction: pair sums, sums of four
     size_t nbuckets = 0;
-    int acc_blocks = 1;
+    int acc_blocks = 1, aff_blocks_g = 1, aff_blocks_d = 1;
 
     int32_t begin(size_t n, size_t cap, cudaStream_t stream, const TableRef* t) {
         s = stream;
@@ -679,11 +827,19 @@ struct MsmJob {
         MPC_ARG_CHECK(n < ((size_t)1 << 31) && cap >= 1 && cap <= n);
         p = make_plan(n, cap, dev->sm_count, use_table ? tbl.c : 0);
         nbuckets = (size_t)p.snwin * p.nb;
-        MPC_ARG_CHECK(p.sn_cap < ((size_t)1 << 31) && (!use_table || (size_t)p.nwin * tbl.stride < ((size_t)1 << 31)));
+        MPC_ARG_CHECK(p.snp < ((size_t)1 << 31) && (!use_table || (size_t)p.nwin * tbl.stride < ((size_t)1 << 31)));
         MPC_ARG_CHECK(nbuckets < ((size_t)1 << 31) && (size_t)p.nwin * cap / p.task_len + nbuckets < ((size_t)1 << 32));
         const uint32_t hbins = 1u << p.hi_bits;
         MPC_TRY(s_digits.alloc(&digits, (size_t)p.nwin * cap, s));
-        MPC_TRY(s_sorted.alloc(&sorted, (size_t)p.nwin * cap, s));
+        MPC_TRY(s_sorted.alloc(&sorted, p.aff ? (size_t)p.snwin * p.snp : (size_t)p.nwin * cap, s));
+        if (p.aff) {
+            MPC_TRY(s_q1.alloc(&q1, (size_t)p.snwin * p.snp / 2, s));
+            if (p.aff > 1) MPC_TRY(s_q2.alloc(&q2, (size_t)p.snwin * p.snp / 4, s));
+            MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aff_blocks_g, k_affine_pairs<F, true>, AFF_THREADS, 0));
+            MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aff_blocks_d, k_affine_pairs<F, false>, AFF_THREADS, 0));
+            if (aff_blocks_g < 1) aff_blocks_g = 1;
+            if (aff_blocks_d < 1) aff_blocks_d = 1;
+        }
         MPC_TRY(s_pairs.alloc(&pairs, (size_t)p.nwin * cap, s));
         MPC_TRY(s_hist.alloc(&hist, (size_t)p.snwin * p.chunks * hbins, s));
         MPC_TRY(s_part.alloc(&part_start, (size_t)p.snwin * (hbins + 1), s));
@@ -701,7 +857,8 @@ struct MsmJob {
         MPC_TRY(s_wpart.alloc(&wpart, (size_t)p.snwin * p.sum_parts, s));
         MPC_TRY(s_wsum.alloc(&wsum, p.snwin, s));
         MPC_CUDA_TRY(cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), s));      // all-zero = infinity
-        MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F>, ACC_THREADS, 0));
+        if (p.aff) MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F, true>, ACC_THREADS, 0));
+        else MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F, false>, ACC_THREADS, 0));
         if (acc_blocks < 1) acc_blocks = 1;
         MPC_TRY(allow_smem(k_finalize_big<F>, ACC_THREADS * sizeof(XYZZ<F>)));
         MPC_TRY(allow_smem(k_window_sum<F>, ACC_THREADS * sizeof(XYZZ<F>)));
@@ -729,8 +886,9 @@ struct MsmJob {
                                                                         pairs, len, use_table ? tbl.stride : 0,
                                                                         use_table ? tbl.offset + done : 0);
         MPC_KERNEL_CHECK();
+        if (p.aff) MPC_CUDA_TRY(cudaMemsetAsync(sorted, 0xff, (size_t)p.snwin * p.snp * sizeof(uint32_t), s));   // holes
         k_sort2<<<dim3(hbins, p.snwin), SORT2_THREADS, (lbins + SORT2_THREADS) * sizeof(uint32_t), s>>>(
-            pairs, part_start, sn, p.lo_bits, hbins, sorted, bstart, bsize);
+            pairs, part_start, sn, p.lo_bits, hbins, sorted, bstart, bsize, p.aff, p.aff ? p.snp : sn);
         MPC_KERNEL_CHECK();
         k_task_sums<<<p.scan_blocks, 1024, 0, s>>>(bsize, nbuckets, p.task_len, bsums);
         MPC_KERNEL_CHECK();
@@ -742,8 +900,30 @@ struct MsmJob {
         profile_end("msm_sort", s);
 
         profile_begin("msm_accumulate", s);
-        k_accumulate<F><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(
-            use_table ? (const Affine<F>*)tbl.table : bases, sorted, sn, p.nb, tasks, counters, buckets, partials, merge);
+        const Affine<F>* points = use_table ? (const Affine<F>*)tbl.table : bases;
+        if (p.aff) {
+            // pairwise affine additions inside every bucket's padded run, then XYZZ accumulation of what is left
+            const size_t slots = (size_t)p.snwin * p.snp;
+            // pairs per lane per shared inversion: at least ~4 batches for every resident warp
+            auto batch_for = [&](size_t npairs, int blocks) {
+                size_t lanes = (size_t)dev->sm_count * blocks * AFF_THREADS;
+                size_t b = npairs / (lanes * 4);
+                return (int)(b < 16 ? 16 : b > AFF_B ? AFF_B : b);
+            };
+            k_affine_pairs<F, true><<<dev->sm_count * aff_blocks_g, AFF_THREADS, 0, s>>>(points, sorted, slots / 2, q1,
+                                                                                    batch_for(slots / 2, aff_blocks_g));
+            MPC_KERNEL_CHECK();
+            if (p.aff > 1) {
+                k_affine_pairs<F, false><<<dev->sm_count * aff_blocks_d, AFF_THREADS, 0, s>>>(q1, nullptr, slots / 4, q2,
+                                                                                         batch_for(slots / 4, aff_blocks_d));
+                MPC_KERNEL_CHECK();
+            }
+            k_accumulate<F, true><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(
+                p.aff > 1 ? q2 : q1, nullptr, p.snp >> p.aff, p.nb, tasks, counters, buckets, partials, merge);
+        } else {
+            k_accumulate<F, false><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(points, sorted, sn, p.nb, tasks, counters,
+                                                                                   buckets, partials, merge);
+        }
         MPC_KERNEL_CHECK();
         profile_end("msm_accumulate", s);
 
@@ -1150,9 +1330,9 @@ int32_t msm_sharded(const BaseSnap& v, size_t offset, const uint64_t* scalars_ho
         size_t lo = std::max(plo, offset), hi = std::min(phi, offset + n);      // this part's share of the range
         if (lo >= hi) continue;
         BaseSnap part = snapshot_of(parent.parts[k]);
-        MPC_TRY(done[k].create());
         DeviceScope scope(part.ref->dev_index);
         MPC_TRY(scope.rc);
+        MPC_TRY(done[k].create());                 // an event records only on streams of the device it was created on
         MPC_TRY(msm_shard_part<F>(part, lo - plo, hi - lo, scalars_host ? scalars_host + (lo - offset) * 4 : nullptr,
                                   scalars_dev ? (const Fr*)scalars_dev[k] : nullptr, gather + k * 3 * N, home_cuda,
                                   home_ready.e, done[k].e, scope.s));
