@@ -290,7 +290,7 @@ def run_gpu(args):
         handle.precompute(0)                            # + 2^(cw)*P table: one shared bucket set
         pre_ms, _ = H.profile_read("msm_precompute")
         H.set_option("profile", 0)
-        tc = 23 if log_n >= 23 else 22 if log_n >= 22 else 20 if log_n >= 20 else 17 if log_n >= 18 else 15
+        tc = 23 if log_n >= 23 else 22 if log_n >= 22 else 20 if log_n >= 20 else 17 if log_n >= 18 else 16 if log_n >= 16 else 15
         table = {"window_bits": tc, "windows": 253 // tc + 1, "bytes": (253 // tc + 1) * n * 96, "precompute_ms": pre_ms}
     scalars_host = pinned(S.fr_uniform(seed + 1000 * rank, n))
     scalars_dev = scalars_host.to("cuda", non_blocking=True)
@@ -358,7 +358,7 @@ def run_gpu(args):
     acc_ms = max_over_ranks(stage_ms["msm_accumulate"])
     achieved = IMAD_PER_POINT * n / (acc_ms * 1e-3) / 1e9
     traffic = Traffic()
-    roofline = {"kernel": "k_accumulate<Fq> (Pippenger bucket accumulation, XYZZ mixed additions)",
+    roofline = {"kernel": "bucket accumulation: k_affine_pairs<Fq> x2 (batched-affine pre-reduction) + k_accumulate<Fq> (XYZZ mixed additions)",
                 "bound": "int32-pipe", "achieved": achieved, "peak": imad_peak, "unit": "GIMAD/s",
                 "frac": achieved / imad_peak, "traffic": traffic.get("k_accumulate", n),
                 "kernel_ms": acc_ms, "share_of_step": acc_ms / ms_per_step,

@@ -66,9 +66,12 @@ for log_n in [int(x) for x in sys.argv[1:]] or [13, 16, 18, 20, 22, 24]:
     except Exception:
         bh, sh = bases_host, sc_host
     for chunks in ([1, 2, 4, 8] if log_n >= 20 else [1]):
-        H.set_option("msm_host_chunks", chunks)
-        w, st = timed(lambda: H.msm_g1(bh, sh), reps=2)
-        row["host_chunks_%d" % chunks] = {"wall_ms": w, "Mpts_s": round(n / w / 1e3, 2), **st}
+        for aff in ((1, 2, 3) if log_n >= 22 else (0,)):
+            H.set_option("msm_host_chunks", chunks)
+            H.set_option("msm_affine", aff)
+            w, st = timed(lambda: H.msm_g1(bh, sh), reps=2)
+            row["host_chunks_%d_affine_%d" % (chunks, aff)] = {"wall_ms": w, "Mpts_s": round(n / w / 1e3, 2), **st}
     H.set_option("msm_host_chunks", 0)
+    H.set_option("msm_affine", 0)
     plain.release(); dev.free(); sc.free(); wl.free(); out.free()
     print(json.dumps(row), flush=True)

@@ -113,7 +113,7 @@ inline Plan make_plan(size_t n, size_t cap, int sm_count, uint32_t table_c) {
         // tools/tune_msm.py (2^24: c = 20, 2^20: c = 17, 2^16: c = 15).  Widths whose top window holds a
         // single bit (253 mod c == 1) are skipped: they put half of a window's entries in one bucket.
         int l = (int)log2_ceil(n);
-        c = l >= 23 ? 20 : l >= 21 ? 19 : l >= 19 ? 17 : l >= 17 ? 16 : l >= 14 ? 15 : l >= 11 ? 11 : l >= 8 ? 8 : 4;
+        c = l >= 23 ? 20 : l >= 21 ? 19 : l >= 19 ? 17 : l >= 17 ? 16 : l >= 14 ? 15 : l >= 11 ? 9 : l >= 8 ? 8 : 4;
     }
     if (c < 3) c = 3;
     if (c > MAX_WINDOW_BITS) c = MAX_WINDOW_BITS;
@@ -901,6 +901,14 @@ struct MsmJob {
 
         profile_begin("msm_accumulate", s);
         const Affine<F>* points = use_table ? (const Affine<F>*)tbl.table : bases;
+        // grids sized by the work of THIS chunk (an upper bound of its task count), not by the machine: the MSMs of
+        // one proof and of the other parties run side by side on their own streams, and a full-machine grid of
+        // mostly idle CTAs in front of them would serialise the small ones
+        const size_t task_bound = ((sn * p.snwin) >> p.aff) / p.task_len + nbuckets + 1;
+        const unsigned acc_grid = (unsigned)std::min<size_t>((size_t)dev->sm_count * acc_blocks,
+                                                             (task_bound + ACC_THREADS - 1) / ACC_THREADS);
+        const unsigned fin_small = (unsigned)std::min<size_t>((size_t)dev->sm_count * 2, (nbuckets + ACC_THREADS - 1) / ACC_THREADS);
+        const unsigned fin_big = (unsigned)std::min<size_t>((size_t)dev->sm_count, nbuckets);
         if (p.aff) {
             // pairwise affine additions inside every bucket's padded run, then XYZZ accumulation of what is left
             const size_t slots = (size_t)p.snwin * p.snp;
@@ -918,20 +926,20 @@ struct MsmJob {
                                                                                          batch_for(slots / 4, aff_blocks_d));
                 MPC_KERNEL_CHECK();
             }
-            k_accumulate<F, true><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(
+            k_accumulate<F, true><<<acc_grid, ACC_THREADS, 0, s>>>(
                 p.aff > 1 ? q2 : q1, nullptr, p.snp >> p.aff, p.nb, tasks, counters, buckets, partials, merge);
         } else {
-            k_accumulate<F, false><<<dev->sm_count * acc_blocks, ACC_THREADS, 0, s>>>(points, sorted, sn, p.nb, tasks, counters,
-                                                                                   buckets, partials, merge);
+            k_accumulate<F, false><<<acc_grid, ACC_THREADS, 0, s>>>(points, sorted, sn, p.nb, tasks, counters, buckets, partials,
+                                                                    merge);
         }
         MPC_KERNEL_CHECK();
         profile_end("msm_accumulate", s);
 
         profile_begin("msm_reduce", s);
-        k_finalize_small<F><<<dev->sm_count * 2, ACC_THREADS, 0, s>>>(small_list, counters, bsize, tstart, p.task_len,
-                                                                      partials, buckets, merge);
+        k_finalize_small<F><<<fin_small, ACC_THREADS, 0, s>>>(small_list, counters, bsize, tstart, p.task_len, partials, buckets,
+                                                              merge);
         MPC_KERNEL_CHECK();
-        k_finalize_big<F><<<dev->sm_count, ACC_THREADS, ACC_THREADS * sizeof(XYZZ<F>), s>>>(
+        k_finalize_big<F><<<fin_big, ACC_THREADS, ACC_THREADS * sizeof(XYZZ<F>), s>>>(
             big_list, counters, bsize, tstart, p.task_len, partials, buckets, merge);
         MPC_KERNEL_CHECK();
         profile_end("msm_reduce", s);
@@ -1103,7 +1111,9 @@ int32_t precompute_one(const BaseSnap& v, uint64_t handle, uint32_t window_bits,
     uint32_t c = window_bits;
     if (c == 0) {
         uint32_t l = log2_ceil(v.n ? v.n : 1);
-        c = l >= 23 ? 23 : l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 15 : l > 7 ? l - 3 : 4;
+        // small vectors are latency-bound (few entries per bucket beat long per-thread chains): tools/tune_msm.py,
+        // 2^13: c = 15 -> 1.08 ms against 1.26 ms at c = 10; 2^16: c = 16 -> 1.87 ms against 2.12 ms at c = 14
+        c = l >= 23 ? 23 : l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 16 : l >= 11 ? 15 : l > 7 ? l - 3 : 4;
         if (msm::SCALAR_BITS % c == 1) c--;       // a one-bit top window would put n/2 entries in one bucket
     }
     uint32_t nwin = msm::num_windows(c);

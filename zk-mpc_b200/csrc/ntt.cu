@@ -560,28 +560,39 @@ int32_t ntt_cross_dev(Fr* data, uint32_t log_n, uint32_t log_g, size_t l0, size_
 }
 
 // ---- one process, g devices: the whole sharded transform -------------------------------------------------
-struct Ev {
-    cudaEvent_t e = nullptr;
-    Ev() {}
-    Ev(const Ev&) = delete;
-    Ev& operator=(const Ev&) = delete;
-    ~Ev() { if (e) cudaEventDestroy(e); }
+// Cross-device barrier: every stream waits until all streams reached this point.  Two phases through the first
+// device's stream (2g waits instead of g^2), events cached per host thread and device (creating and destroying
+// them per call costs more than the barrier).  Reusing an event is safe: a later record can only be issued after
+// the host enqueued every wait on the earlier one, and a wait captures the record that precedes it.
+struct EvCache {
+    cudaEvent_t arrive[64] = {}, release = nullptr;
+    int release_dev = -1;
 };
+thread_local EvCache t_ev;
 
-// every stream waits until all streams reached this point
-int32_t cross_barrier(const int* dev, cudaStream_t* st, Ev* evs, int g) {
-    for (int q = 0; q < g; q++) {
+int32_t cross_barrier(const int* dev, cudaStream_t* st, int g) {
+    bool distinct = false;
+    for (int q = 1; q < g; q++) distinct = distinct || st[q] != st[0];
+    if (!distinct) return MPC_CUDA_OK;               // one stream: already ordered
+    for (int q = 1; q < g; q++) {
         DeviceScope scope(dev[q]);
         MPC_TRY(scope.rc);
-        if (!evs[q].e) MPC_CUDA_TRY(cudaEventCreateWithFlags(&evs[q].e, cudaEventDisableTiming));
-        MPC_CUDA_TRY(cudaEventRecord(evs[q].e, st[q]));
+        cudaEvent_t& e = t_ev.arrive[dev[q]];
+        if (!e) MPC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        MPC_CUDA_TRY(cudaEventRecord(e, st[q]));
     }
-    for (int q = 0; q < g; q++) {
-        DeviceScope scope(dev[q]);
+    {
+        DeviceScope scope(dev[0]);
         MPC_TRY(scope.rc);
-        for (int r = 0; r < g; r++)
-            if (r != q && st[r] != st[q]) MPC_CUDA_TRY(cudaStreamWaitEvent(st[q], evs[r].e, 0));
+        for (int q = 1; q < g; q++) MPC_CUDA_TRY(cudaStreamWaitEvent(st[0], t_ev.arrive[dev[q]], 0));
+        if (t_ev.release && t_ev.release_dev != dev[0]) { cudaEventDestroy(t_ev.release); t_ev.release = nullptr; }
+        if (!t_ev.release) {
+            MPC_CUDA_TRY(cudaEventCreateWithFlags(&t_ev.release, cudaEventDisableTiming));
+            t_ev.release_dev = dev[0];
+        }
+        MPC_CUDA_TRY(cudaEventRecord(t_ev.release, st[0]));
     }
+    for (int q = 1; q < g; q++) MPC_CUDA_TRY(cudaStreamWaitEvent(st[q], t_ev.release, 0));
     return MPC_CUDA_OK;
 }
 
@@ -611,7 +622,6 @@ int32_t ntt_sharded_dev(Fr* const* blocks, const int32_t* dev_index, uint32_t lo
         st[q] = scope.s;
     }
     const size_t m = (size_t)1 << (log_n - log_g), slice = m >> log_g;
-    Ev ev_a[1 << MAX_LOG_G], ev_b[1 << MAX_LOG_G], ev_c[1 << MAX_LOG_G];
     if (inverse) {
         for (int q = 0; q < g; q++) {
             DeviceScope scope(dev[q]);
@@ -619,20 +629,20 @@ int32_t ntt_sharded_dev(Fr* const* blocks, const int32_t* dev_index, uint32_t lo
             MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_IFFT, 1, st[q]));
         }
     }
-    MPC_TRY(cross_barrier(dev, st, ev_a, g));          // every block is ready to be read by every device
+    MPC_TRY(cross_barrier(dev, st, g));          // every block is ready to be read by every device
     for (int r = 0; r < g; r++) {
         DeviceScope scope(dev[r]);
         MPC_TRY(scope.rc);
         MPC_TRY(ntt_cross_launch(blocks, 0, log_n, log_g, (size_t)r * slice, slice, kind, st[r]));
     }
-    MPC_TRY(cross_barrier(dev, st, ev_b, g));          // every block received the stores of every device
+    MPC_TRY(cross_barrier(dev, st, g));          // every block received the stores of every device
     if (!inverse) {
         for (int q = 0; q < g; q++) {
             DeviceScope scope(dev[q]);
             MPC_TRY(scope.rc);
             MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_FFT, 1, st[q]));
         }
-        MPC_TRY(cross_barrier(dev, st, ev_c, g));      // the first device's stream now orders after the whole job
+        MPC_TRY(cross_barrier(dev, st, g));      // the first device's stream now orders after the whole job
     }
     return MPC_CUDA_OK;
 }
@@ -678,8 +688,7 @@ int32_t ntt_reorder_sharded(Fr* const* in, Fr* const* out, const int32_t* dev_in
         MPC_TRY(scope.rc);
         st[q] = scope.s;
     }
-    Ev ev_a[1 << MAX_LOG_G], ev_b[1 << MAX_LOG_G];
-    MPC_TRY(cross_barrier(dev, st, ev_a, g));
+    MPC_TRY(cross_barrier(dev, st, g));
     const size_t m = (size_t)1 << (log_n - log_g);
     for (int q = 0; q < g; q++) {
         DeviceScope scope(dev[q]);
@@ -691,7 +700,7 @@ int32_t ntt_reorder_sharded(Fr* const* in, Fr* const* out, const int32_t* dev_in
         k_ntt_reorder<<<(unsigned)((m + 255) / 256), 256, 0, st[q]>>>(a);
         MPC_KERNEL_CHECK();
     }
-    return cross_barrier(dev, st, ev_b, g);
+    return cross_barrier(dev, st, g);
 }
 
 }  // namespace
