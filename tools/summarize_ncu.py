@@ -41,7 +41,7 @@ def main():
             if os.path.exists(src):
                 shutil.copy(src, os.path.join(ROOT, "profiles", "%s_%s%s" % (tag, cap, ext)))
     json.dump(summary, open(os.path.join(ROOT, "profiles", "%s_ncu_summary.json" % tag), "w"), indent=1)
-    tr = {k: {"bytes_per_unit": sum(v) / len(v), "capture_log_n": log_n, "launches": len(v),
+    tr = {k: {"bytes_per_unit": sum(v) / len(v), "bytes_per_unit_all_launches": sum(v), "capture_log_n": log_n, "launches": len(v),
               "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch / 2^%d" % log_n}
           for k, v in traffic.items()}
     json.dump(tr, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)

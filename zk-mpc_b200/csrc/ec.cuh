@@ -303,4 +303,16 @@ DEV void xyzz_add_warp(XYZZ<F>& p, const XYZZ<F>& q) {
     p.zz = r3[2];
     p.zzz = r4[2];
 }
+
+// k * q for a small unsigned multiplier, warp-cooperative (double-and-add, MSB first)
+template <class F>
+DEV XYZZ<F> xyzz_mul_small_warp(const XYZZ<F>& q, uint64_t k) {
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    bool started = false;
+    for (int i = 63; i >= 0; i--) {
+        if (started) xyzz_dbl_warp(acc);
+        if ((k >> i) & 1) { xyzz_add_warp(acc, q); started = true; }
+    }
+    return acc;
+}
 #endif

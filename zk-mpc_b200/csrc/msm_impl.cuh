@@ -494,35 +494,62 @@ constexpr int AFF_THREADS = 128;
 template <class F>
 DEV bool aff_none(const Affine<F>& p) { return p.x.is_zero() && p.y.is_zero(); }
 
-// kind: 0 nothing, 1 first only, 2 second only, 3 chord, 4 tangent; d = the denominator to invert (1 if none)
-template <class F, bool GATHER>
+// x coordinate only (first half of the affine point): all the forward pass needs unless the two x agree
+template <class F>
+DEV F load_x_ro(const Affine<F>* p) {
+    static_assert(sizeof(F) % 16 == 0, "size");
+    F r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(F) / 16); i++) {
+        uint4 t = __ldg(q + i);
+        w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+    }
+    return r;
+}
+
+// kind: 0 nothing, 1 first only, 2 second only, 3 chord, 4 tangent; d = the denominator to invert (1 if none).
+// FULL = false (forward pass): only d is produced, from the x coordinates alone; the y coordinates (a sign flips
+// only y) are fetched just when the x agree.  FULL = true (backward pass): a and b are complete.
+template <class F, bool GATHER, bool FULL>
 DEV int aff_load_pair(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, size_t i, size_t npairs,
                       Affine<F>& a, Affine<F>& b, F& d) {
     d = F::one();
     if (i >= npairs) return 0;
     bool va, vb;
+    const Affine<F>*pa, *pb;
+    bool na = false, nb = false;
     if (GATHER) {
         uint2 e = __ldg(reinterpret_cast<const uint2*>(idx) + i);
         va = e.x != 0xffffffffu;
         vb = e.y != 0xffffffffu;
-        if (va) {
-            a = load_pod_ro(pts + (e.x & ~msm::DIGIT_NEG));
-            if (e.x & msm::DIGIT_NEG) a.y = neg(a.y);
-        }
-        if (vb) {
-            b = load_pod_ro(pts + (e.y & ~msm::DIGIT_NEG));
-            if (e.y & msm::DIGIT_NEG) b.y = neg(b.y);
-        }
+        pa = pts + (e.x & ~msm::DIGIT_NEG);
+        pb = pts + (e.y & ~msm::DIGIT_NEG);
+        na = (e.x & msm::DIGIT_NEG) != 0;
+        nb = (e.y & msm::DIGIT_NEG) != 0;
     } else {
-        a = load_pod_ro(pts + 2 * i);
-        b = load_pod_ro(pts + 2 * i + 1);
-        va = !aff_none(a);
-        vb = !aff_none(b);
+        pa = pts + 2 * i;
+        pb = pts + 2 * i + 1;
+        va = vb = true;                          // decided from the loaded values below
+    }
+    if (FULL || !GATHER) {
+        // dense inputs carry their validity in the value ((0, 0) = none), so they are always read whole
+        if (va) { a = load_pod_ro(pa); if (na) a.y = neg(a.y); }
+        if (vb) { b = load_pod_ro(pb); if (nb) b.y = neg(b.y); }
+        if (!GATHER) { va = !aff_none(a); vb = !aff_none(b); }
+    } else {
+        if (va) a.x = load_x_ro(pa);
+        if (vb) b.x = load_x_ro(pb);
     }
     if (!va) return vb ? 2 : 0;
     if (!vb) return 1;
     F dx = sub(b.x, a.x);
     if (!dx.is_zero()) { d = dx; return 3; }
+    if (!(FULL || !GATHER)) {                    // rare: same x, the y decide between tangent and infinity
+        a = load_pod_ro(pa); if (na) a.y = neg(a.y);
+        b = load_pod_ro(pb); if (nb) b.y = neg(b.y);
+    }
     if (a.y == b.y && !a.y.is_zero()) { d = dbl(a.y); return 4; }
     return 0;                                   // P + (-P) (or a 2-torsion point doubled): the point at infinity
 }
@@ -542,7 +569,7 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* _
         for (int k = 0; k < batch; k++) {
             Affine<F> a, b;
             F d;
-            aff_load_pair<F, GATHER>(pts, idx, base + (size_t)k * 32 + lane, npairs, a, b, d);
+            aff_load_pair<F, GATHER, false>(pts, idx, base + (size_t)k * 32 + lane, npairs, a, b, d);
             pre[k] = run;
             run = mul(run, d);
         }
@@ -563,7 +590,7 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* _
             const size_t i = base + (size_t)k * 32 + lane;
             Affine<F> a, b, r;
             F d;
-            int kind = aff_load_pair<F, GATHER>(pts, idx, i, npairs, a, b, d);
+            int kind = aff_load_pair<F, GATHER, true>(pts, idx, i, npairs, a, b, d);
             F dinv = mul(inv_run, pre[k]);
             inv_run = mul(inv_run, d);
             if (kind >= 3) {
@@ -669,6 +696,30 @@ __global__ void __launch_bounds__(ACC_THREADS) k_bucket_reduce(const XYZZ<F>* __
         xyzz_add(acc, s);
     }
     store_pod(chunk_res + id, acc);
+}
+
+// The same with one WARP per chunk (ec.cuh, warp-cooperative group law): for small MSMs, where the chunk count
+// cannot fill the machine anyway and the running-sum chain is pure latency (5 product latencies per addition
+// instead of 14, 3 per doubling instead of 9).
+template <class F>
+__global__ void __launch_bounds__(ACC_THREADS) k_bucket_reduce_warp(const XYZZ<F>* __restrict__ buckets, uint32_t nwin,
+                                                                    uint32_t nb, uint32_t m, uint32_t T,
+                                                                    XYZZ<F>* __restrict__ chunk_res) {
+    uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (id >= nwin * T) return;                    // whole warps leave together
+    uint32_t w = id / T, t = id % T;
+    const XYZZ<F>* b = buckets + (size_t)w * nb + (size_t)t * m;
+    XYZZ<F> running = XYZZ<F>::infinity(), acc = XYZZ<F>::infinity();
+    for (uint32_t j = m; j-- > 0;) {
+        XYZZ<F> q = load_pod(b + j);
+        xyzz_add_warp(running, q);
+        xyzz_add_warp(acc, running);
+    }
+    if (t) {
+        XYZZ<F> s = xyzz_mul_small_warp(running, (uint64_t)t * m);
+        xyzz_add_warp(acc, s);
+    }
+    if ((threadIdx.x & 31) == 0) store_pod(chunk_res + id, acc);
 }
 
 // block (part, w) sums items [part*len, (part+1)*len) of window w's `count` inputs -> out[w*parts + part]
@@ -952,8 +1003,13 @@ struct MsmJob {
         profile_begin("msm_reduce", s);
         const size_t tree_smem = ACC_THREADS * sizeof(XYZZ<F>);
         uint32_t red_threads = p.snwin * p.red_t;
-        k_bucket_reduce<F><<<(red_threads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(buckets, p.snwin, p.nb,
-                                                                                                p.red_m, p.red_t, chunk_res);
+        if (red_threads <= 1024) {                 // one wave of warps (255 registers: ~8 warps per SM)
+            k_bucket_reduce_warp<F><<<(red_threads * 32 + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(
+                buckets, p.snwin, p.nb, p.red_m, p.red_t, chunk_res);
+        } else {
+            k_bucket_reduce<F><<<(red_threads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(buckets, p.snwin, p.nb,
+                                                                                                    p.red_m, p.red_t, chunk_res);
+        }
         MPC_KERNEL_CHECK();
         if (p.sum_parts == 1) {
             k_window_sum<F><<<dim3(1, p.snwin), ACC_THREADS, tree_smem, s>>>(chunk_res, p.red_t, p.red_t, wsum);
@@ -1111,9 +1167,11 @@ int32_t precompute_one(const BaseSnap& v, uint64_t handle, uint32_t window_bits,
     uint32_t c = window_bits;
     if (c == 0) {
         uint32_t l = log2_ceil(v.n ? v.n : 1);
-        // small vectors are latency-bound (few entries per bucket beat long per-thread chains): tools/tune_msm.py,
-        // 2^13: c = 15 -> 1.08 ms against 1.26 ms at c = 10; 2^16: c = 16 -> 1.87 ms against 2.12 ms at c = 14
-        c = l >= 23 ? 23 : l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 16 : l >= 11 ? 15 : l > 7 ? l - 3 : 4;
+        // small vectors are latency-bound (few entries per bucket beat long per-thread chains, and 2^(c-1) / 4 <= 1024
+        // chunks keep the warp-cooperative bucket reduction in one wave): tools/tune_msm.py, 2^13: G1 c = 13 -> 0.98 ms
+        // (c = 10: 1.26 ms before), G2 c = 12 -> 2.75 ms (c = 10: 3.3 ms); 2^16: c = 16 -> 1.87 ms (c = 14: 2.12 ms)
+        const uint32_t small_c = sizeof(F) > 48 ? 12 : 13;
+        c = l >= 23 ? 23 : l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 16 : l >= 11 ? small_c : l > 7 ? l - 3 : 4;
         if (msm::SCALAR_BITS % c == 1) c--;       // a one-bit top window would put n/2 entries in one bucket
     }
     uint32_t nwin = msm::num_windows(c);
