@@ -554,6 +554,31 @@ DEV int aff_load_pair(const Affine<F>* __restrict__ pts, const uint32_t* __restr
     return 0;                                   // P + (-P) (or a 2-torsion point doubled): the point at infinity
 }
 
+// Pull the two operands of pair i towards L2 a few iterations before they are needed: the gathers are random
+// 96-byte reads from a multi-GB table, and a lane has only ~5 products of work to hide each DRAM round trip.
+template <class F, bool GATHER>
+DEV void aff_prefetch_pair(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, size_t i, size_t npairs,
+                           bool whole) {
+    if (i >= npairs) return;
+    const char *pa, *pb;
+    if (GATHER) {
+        uint2 e = __ldg(reinterpret_cast<const uint2*>(idx) + i);
+        if (e.x == 0xffffffffu) return;
+        pa = reinterpret_cast<const char*>(pts + (e.x & ~msm::DIGIT_NEG));
+        pb = e.y == 0xffffffffu ? pa : reinterpret_cast<const char*>(pts + (e.y & ~msm::DIGIT_NEG));
+    } else {
+        pa = reinterpret_cast<const char*>(pts + 2 * i);
+        pb = pa + sizeof(Affine<F>);
+    }
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pb));
+    if (whole) {                                  // the far end of the point may sit in the next line
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + sizeof(Affine<F>) - 16));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + sizeof(Affine<F>) - 16));
+    }
+}
+constexpr int AFF_PREFETCH = 3;                   // iterations ahead
+
 // `batch` (<= AFF_B) pairs per lane share one inversion: long batches amortise it, short ones keep every warp of
 // the machine busy on small inputs (chosen by the host from the pair count)
 template <class F, bool GATHER>
@@ -569,6 +594,8 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* _
         for (int k = 0; k < batch; k++) {
             Affine<F> a, b;
             F d;
+            if (k + AFF_PREFETCH < batch)
+                aff_prefetch_pair<F, GATHER>(pts, idx, base + (size_t)(k + AFF_PREFETCH) * 32 + lane, npairs, !GATHER);
             aff_load_pair<F, GATHER, false>(pts, idx, base + (size_t)k * 32 + lane, npairs, a, b, d);
             pre[k] = run;
             run = mul(run, d);
@@ -590,6 +617,7 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* _
             const size_t i = base + (size_t)k * 32 + lane;
             Affine<F> a, b, r;
             F d;
+            if (k >= AFF_PREFETCH) aff_prefetch_pair<F, GATHER>(pts, idx, i - (size_t)AFF_PREFETCH * 32, npairs, true);
             int kind = aff_load_pair<F, GATHER, true>(pts, idx, i, npairs, a, b, d);
             F dinv = mul(inv_run, pre[k]);
             inv_run = mul(inv_run, d);
@@ -1003,7 +1031,8 @@ struct MsmJob {
         profile_begin("msm_reduce", s);
         const size_t tree_smem = ACC_THREADS * sizeof(XYZZ<F>);
         uint32_t red_threads = p.snwin * p.red_t;
-        if (red_threads <= 1024) {                 // one wave of warps (255 registers: ~8 warps per SM)
+        if (red_threads <= 128) {                  // 32x the threads: only while that stays a sliver of the machine,
+                                                   // the MSMs of one proof and of the other parties run concurrently
             k_bucket_reduce_warp<F><<<(red_threads * 32 + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(
                 buckets, p.snwin, p.nb, p.red_m, p.red_t, chunk_res);
         } else {
@@ -1167,10 +1196,10 @@ int32_t precompute_one(const BaseSnap& v, uint64_t handle, uint32_t window_bits,
     uint32_t c = window_bits;
     if (c == 0) {
         uint32_t l = log2_ceil(v.n ? v.n : 1);
-        // small vectors are latency-bound (few entries per bucket beat long per-thread chains, and 2^(c-1) / 4 <= 1024
-        // chunks keep the warp-cooperative bucket reduction in one wave): tools/tune_msm.py, 2^13: G1 c = 13 -> 0.98 ms
-        // (c = 10: 1.26 ms before), G2 c = 12 -> 2.75 ms (c = 10: 3.3 ms); 2^16: c = 16 -> 1.87 ms (c = 14: 2.12 ms)
-        const uint32_t small_c = sizeof(F) > 48 ? 12 : 13;
+        // small vectors are latency-bound; what counts for a proof is several of them running side by side (4 MSMs x
+        // 3 parties): tools/tune_msm.py + bench.py extra.prove with PK_BITS_G1/G2, domain 2^13: c = 12 for both groups
+        // gives the shortest 3-party prove (10.1 ms; c = 10: 11.9 ms), single MSMs 1.1 ms (G1) / 3.4 ms (G2)
+        const uint32_t small_c = 12;
         c = l >= 23 ? 23 : l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 16 : l >= 11 ? small_c : l > 7 ? l - 3 : 4;
         if (msm::SCALAR_BITS % c == 1) c--;       // a one-bit top window would put n/2 entries in one bucket
     }

@@ -43,7 +43,7 @@ class ProvingKey:
     """
 
     def __init__(self, a_query, b_g1_query, b_g2_query, h_query, l_query, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2,
-                 precompute=True):
+                 precompute=True, table_bits_g1=0, table_bits_g2=0):
         def flags(q):
             pts, inf = q
             return np.zeros(len(pts), dtype=np.uint8) if inf is None else np.asarray(inf, dtype=np.uint8)
@@ -68,7 +68,7 @@ class ProvingKey:
         self.LH = H.register_bases(blh, inf=np.concatenate([flags(l_query), flags(h_query)]))
         if precompute:                                       # the CRS is fixed per circuit: window tables pay off
             for h in (self.A, self.B1, self.B2, self.LH):
-                h.precompute(0)
+                h.precompute(table_bits_g2 if h.g2 else table_bits_g1)     # 0 = the library's choice for the size
 
     def release(self):
         for h in (self.A, self.B1, self.B2, self.LH):
