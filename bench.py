@@ -292,7 +292,7 @@ def run_gpu(args):
         handle.precompute(0)                            # + 2^(cw)*P table: one shared bucket set
         pre_ms, _ = H.profile_read("msm_precompute")
         H.set_option("profile", 0)
-        tc = 23 if log_n >= 23 else 22 if log_n >= 22 else 20 if log_n >= 20 else 17 if log_n >= 18 else 16 if log_n >= 16 else 12
+        tc = 22 if log_n >= 22 else 20 if log_n >= 20 else 17 if log_n >= 18 else 16 if log_n >= 16 else 12
         table = {"window_bits": tc, "windows": 253 // tc + 1, "bytes": (253 // tc + 1) * n * 96, "precompute_ms": pre_ms}
     scalars_host = pinned(S.fr_uniform(seed + 1000 * rank, n))
     scalars_dev = scalars_host.to("cuda", non_blocking=True)

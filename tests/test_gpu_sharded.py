@@ -25,7 +25,7 @@ def H(pkg):
 @pytest.fixture(autouse=True)
 def _reset_options(H):
     yield
-    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks", "msm_affine"):
+    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks", "msm_affine", "ntt_graph"):
         H.set_option(name, 0)
 
 
@@ -413,3 +413,34 @@ def test_g1_affine_prereduction_full_size_exact(H, orc, pkg):
     wl = pkg.synth.fr_witness_like(seed + 1, n)
     assert _same(H.msm_handle(h, wl), helpers.expected_msm_of_generated(orc, wl, ks))
     h.release(); dev.free()
+
+
+@pytest.mark.parametrize("log_g", [1, 3])
+def test_sharded_ntt_replayed_from_a_cuda_graph(H, orc, pkg, log_g):
+    """repeated sharded transforms over the same blocks: first call direct, second captured into a CUDA graph,
+    later ones replayed — every call bit-exact on fresh data (virtual devices, option ntt_graph = 1)"""
+    g = 1 << log_g
+    H.set_option("ntt_graph", 1)
+    try:
+        for log_n in (10, 17):               # one local pass / several local passes (ping-pong buffer in the graph)
+            n = 1 << log_n
+            m = n // g
+            bufs = [H.DeviceBuffer(m * 32) for _ in range(g)]
+            for kind in ("fft", "coset_ifft"):
+                inverse = kind == "coset_ifft"
+                for rep in range(4):
+                    full = pkg.synth.fr_uniform(0xC00 + 16 * log_n + rep, n)
+                    expect = orc.ntt(full, kind)
+                    for r in range(g):
+                        bufs[r].upload(full[np.arange(m) * g + _bitrev(r, log_g)] if inverse else full[r * m:(r + 1) * m])
+                    H.ntt_sharded_dev([b.ptr.value for b in bufs], log_n, kind, dev_index=[0] * g)
+                    out = [b.download().reshape(m, 4) for b in bufs]
+                    if inverse:
+                        assert np.array_equal(np.concatenate(out), expect), (log_n, kind, rep)
+                    else:
+                        for r in range(g):
+                            assert np.array_equal(out[r], expect[np.arange(m) * g + _bitrev(r, log_g)]), (log_n, kind, rep, r)
+            for b in bufs:
+                b.free()
+    finally:
+        H.set_option("ntt_graph", 0)

@@ -101,6 +101,7 @@ extern std::atomic<int64_t> g_opt_msm_affine;
 extern std::atomic<int64_t> g_opt_profile;
 extern std::atomic<int64_t> g_opt_ntt_generic;
 extern std::atomic<int64_t> g_opt_ntt_occupancy;
+extern std::atomic<int64_t> g_opt_ntt_graph;
 
 inline cudaStream_t pick_stream(void* user, cudaStream_t mine) { return user ? (cudaStream_t)user : mine; }
 

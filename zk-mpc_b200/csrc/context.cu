@@ -282,6 +282,9 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "ntt_occupancy")) {
         MPC_ARG_CHECK(value >= 0 && value <= 2);
         g_opt_ntt_occupancy = value;
+    } else if (!strcmp(name, "ntt_graph")) {
+        MPC_ARG_CHECK(value >= 0 && value <= 2);
+        g_opt_ntt_graph = value;
     } else if (!strcmp(name, "ntt_generic")) {
         g_opt_ntt_generic = value ? 1 : 0;
     } else if (!strcmp(name, "msm_affine")) {

@@ -554,31 +554,6 @@ DEV int aff_load_pair(const Affine<F>* __restrict__ pts, const uint32_t* __restr
     return 0;                                   // P + (-P) (or a 2-torsion point doubled): the point at infinity
 }
 
-// Pull the two operands of pair i towards L2 a few iterations before they are needed: the gathers are random
-// 96-byte reads from a multi-GB table, and a lane has only ~5 products of work to hide each DRAM round trip.
-template <class F, bool GATHER>
-DEV void aff_prefetch_pair(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, size_t i, size_t npairs,
-                           bool whole) {
-    if (i >= npairs) return;
-    const char *pa, *pb;
-    if (GATHER) {
-        uint2 e = __ldg(reinterpret_cast<const uint2*>(idx) + i);
-        if (e.x == 0xffffffffu) return;
-        pa = reinterpret_cast<const char*>(pts + (e.x & ~msm::DIGIT_NEG));
-        pb = e.y == 0xffffffffu ? pa : reinterpret_cast<const char*>(pts + (e.y & ~msm::DIGIT_NEG));
-    } else {
-        pa = reinterpret_cast<const char*>(pts + 2 * i);
-        pb = pa + sizeof(Affine<F>);
-    }
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(pb));
-    if (whole) {                                  // the far end of the point may sit in the next line
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + sizeof(Affine<F>) - 16));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + sizeof(Affine<F>) - 16));
-    }
-}
-constexpr int AFF_PREFETCH = 3;                   // iterations ahead
-
 // `batch` (<= AFF_B) pairs per lane share one inversion: long batches amortise it, short ones keep every warp of
 // the machine busy on small inputs (chosen by the host from the pair count)
 template <class F, bool GATHER>
@@ -594,8 +569,6 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* _
         for (int k = 0; k < batch; k++) {
             Affine<F> a, b;
             F d;
-            if (k + AFF_PREFETCH < batch)
-                aff_prefetch_pair<F, GATHER>(pts, idx, base + (size_t)(k + AFF_PREFETCH) * 32 + lane, npairs, !GATHER);
             aff_load_pair<F, GATHER, false>(pts, idx, base + (size_t)k * 32 + lane, npairs, a, b, d);
             pre[k] = run;
             run = mul(run, d);
@@ -617,7 +590,6 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* _
             const size_t i = base + (size_t)k * 32 + lane;
             Affine<F> a, b, r;
             F d;
-            if (k >= AFF_PREFETCH) aff_prefetch_pair<F, GATHER>(pts, idx, i - (size_t)AFF_PREFETCH * 32, npairs, true);
             int kind = aff_load_pair<F, GATHER, true>(pts, idx, i, npairs, a, b, d);
             F dinv = mul(inv_run, pre[k]);
             inv_run = mul(inv_run, d);
@@ -1200,7 +1172,8 @@ int32_t precompute_one(const BaseSnap& v, uint64_t handle, uint32_t window_bits,
         // 3 parties): tools/tune_msm.py + bench.py extra.prove with PK_BITS_G1/G2, domain 2^13: c = 12 for both groups
         // gives the shortest 3-party prove (10.1 ms; c = 10: 11.9 ms), single MSMs 1.1 ms (G1) / 3.4 ms (G2)
         const uint32_t small_c = 12;
-        c = l >= 23 ? 23 : l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 16 : l >= 11 ? small_c : l > 7 ? l - 3 : 4;
+        // 2^24 with the affine pre-reduction: c = 22 -> 78.3 ms, c = 23 -> 80.0 ms (both 12 windows; half the buckets)
+        c = l >= 22 ? 22 : l >= 20 ? 20 : l >= 18 ? 17 : l >= 16 ? 16 : l >= 11 ? small_c : l > 7 ? l - 3 : 4;
         if (msm::SCALAR_BITS % c == 1) c--;       // a one-bit top window would put n/2 entries in one bucket
     }
     uint32_t nwin = msm::num_windows(c);

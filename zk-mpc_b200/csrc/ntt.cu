@@ -17,6 +17,7 @@
 // sub-transforms whose bit-reversed destinations are adjacent, so its stores are 128-byte runs too,
 // and fuses the n⁻¹ / coset scaling.  The index algebra is modelled and tested in tests/ntt_model.py.
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -24,7 +25,8 @@ using namespace mpc;
 
 namespace mpc {
 std::atomic<int64_t> g_opt_ntt_occupancy{0};    // 1: the pass kernels compiled for one more CTA per SM
-std::atomic<int64_t> g_opt_ntt_generic{0};      // 1: always run the generic pass kernel (A/B measurements, tests)
+std::atomic<int64_t> g_opt_ntt_generic{0};
+std::atomic<int64_t> g_opt_ntt_graph{0};        // sharded NTT replay through CUDA graphs: 0 auto, 1 always, 2 never      // 1: always run the generic pass kernel (A/B measurements, tests)
 }
 
 namespace {
@@ -371,7 +373,8 @@ int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s,
     return MPC_CUDA_OK;
 }
 
-int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStream_t s) {
+// tmp_override: caller-owned ping-pong buffer of n * batch elements (the captured multi-GPU path must not allocate)
+int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStream_t s, Fr* tmp_override = nullptr) {
     MPC_ARG_CHECK(kind <= MPC_CUDA_NTT_COSET_IFFT);
     MPC_ARG_CHECK(log_n <= MAX_LOG_N && log_n <= (uint32_t)consts::FR_TWO_ADICITY);
     if (batch == 0) return MPC_CUDA_OK;
@@ -388,8 +391,8 @@ int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStr
     uint32_t npass = (log_n + NTT_MAX_DEG - 1) / NTT_MAX_DEG;
     uint32_t base = log_n / npass, extra = log_n % npass;
     Scratch stmp;
-    Fr* tmp = nullptr;
-    if (npass > 1) MPC_TRY(stmp.alloc(&tmp, n * batch, s));
+    Fr* tmp = tmp_override;
+    if (npass > 1 && !tmp) MPC_TRY(stmp.alloc(&tmp, n * batch, s));
 
     uint32_t s0 = 0;
     for (uint32_t p = 0; p < npass; p++) {
@@ -570,21 +573,28 @@ struct EvCache {
 };
 thread_local EvCache t_ev;
 
-int32_t cross_barrier(const int* dev, cudaStream_t* st, int g) {
+// mode: BAR_FULL everyone waits for everyone; BAR_JOIN only the first stream waits for the others (end of a
+// captured graph); BAR_FORK only the others wait for the first stream (start of a captured graph)
+enum { BAR_FULL = 0, BAR_JOIN = 1, BAR_FORK = 2 };
+int32_t cross_barrier(const int* dev, cudaStream_t* st, int g, int mode = BAR_FULL) {
     bool distinct = false;
     for (int q = 1; q < g; q++) distinct = distinct || st[q] != st[0];
     if (!distinct) return MPC_CUDA_OK;               // one stream: already ordered
-    for (int q = 1; q < g; q++) {
-        DeviceScope scope(dev[q]);
-        MPC_TRY(scope.rc);
-        cudaEvent_t& e = t_ev.arrive[dev[q]];
-        if (!e) MPC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        MPC_CUDA_TRY(cudaEventRecord(e, st[q]));
+    if (mode != BAR_FORK) {
+        for (int q = 1; q < g; q++) {
+            DeviceScope scope(dev[q]);
+            MPC_TRY(scope.rc);
+            cudaEvent_t& e = t_ev.arrive[dev[q]];
+            if (!e) MPC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            MPC_CUDA_TRY(cudaEventRecord(e, st[q]));
+        }
     }
     {
         DeviceScope scope(dev[0]);
         MPC_TRY(scope.rc);
-        for (int q = 1; q < g; q++) MPC_CUDA_TRY(cudaStreamWaitEvent(st[0], t_ev.arrive[dev[q]], 0));
+        if (mode != BAR_FORK)
+            for (int q = 1; q < g; q++) MPC_CUDA_TRY(cudaStreamWaitEvent(st[0], t_ev.arrive[dev[q]], 0));
+        if (mode == BAR_JOIN) return MPC_CUDA_OK;
         if (t_ev.release && t_ev.release_dev != dev[0]) { cudaEventDestroy(t_ev.release); t_ev.release = nullptr; }
         if (!t_ev.release) {
             MPC_CUDA_TRY(cudaEventCreateWithFlags(&t_ev.release, cudaEventDisableTiming));
@@ -594,6 +604,70 @@ int32_t cross_barrier(const int* dev, cudaStream_t* st, int g) {
     }
     for (int q = 1; q < g; q++) MPC_CUDA_TRY(cudaStreamWaitEvent(st[q], t_ev.release, 0));
     return MPC_CUDA_OK;
+}
+
+// the launches of one sharded transform.  captured = true: the streams are being captured into a CUDA graph from
+// the first stream: fork at the start, join at the end, no allocation (tmp[q] = ping-pong buffer on device q).
+int32_t ntt_sharded_body(Fr* const* blocks, const int* dev, cudaStream_t* st, int g, uint32_t log_n, uint32_t log_g,
+                         uint32_t kind, Fr* const* tmp, bool captured) {
+    const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
+    const size_t m = (size_t)1 << (log_n - log_g), slice = m >> log_g;
+    if (captured) MPC_TRY(cross_barrier(dev, st, g, BAR_FORK));
+    if (inverse) {
+        for (int q = 0; q < g; q++) {
+            DeviceScope scope(dev[q]);
+            MPC_TRY(scope.rc);
+            MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_IFFT, 1, st[q], tmp ? tmp[q] : nullptr));
+        }
+    }
+    if (!captured || inverse) MPC_TRY(cross_barrier(dev, st, g));      // every block is ready to be read by every device
+    for (int r = 0; r < g; r++) {
+        DeviceScope scope(dev[r]);
+        MPC_TRY(scope.rc);
+        MPC_TRY(ntt_cross_launch(blocks, 0, log_n, log_g, (size_t)r * slice, slice, kind, st[r]));
+    }
+    // every block received the stores of every device
+    MPC_TRY(cross_barrier(dev, st, g, inverse && captured ? BAR_JOIN : BAR_FULL));
+    if (!inverse) {
+        for (int q = 0; q < g; q++) {
+            DeviceScope scope(dev[q]);
+            MPC_TRY(scope.rc);
+            MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_FFT, 1, st[q], tmp ? tmp[q] : nullptr));
+        }
+        // the first device's stream now orders after the whole job
+        MPC_TRY(cross_barrier(dev, st, g, captured ? BAR_JOIN : BAR_FULL));
+    }
+    return MPC_CUDA_OK;
+}
+
+// A sharded transform is ~170 driver calls from one host thread (8 devices x (cross stage + 3 passes) + the event
+// barriers), about as long as the GPU work itself at 2^24 over 8 GPUs.  Repeated transforms of the same blocks
+// (witness_map runs seven per proof over the same buffers) are therefore replayed from a CUDA graph captured across
+// the devices' streams: first call direct (builds tables, sets attributes), second call captured, later calls one
+// cudaGraphLaunch between two small real barriers that order it against the other streams' earlier / later work.
+struct ShardKey {
+    Fr* blocks[1 << MAX_LOG_G];
+    int dev[1 << MAX_LOG_G];
+    uint32_t log_n, log_g, kind;
+    bool operator==(const ShardKey& o) const { return memcmp(this, &o, sizeof(ShardKey)) == 0; }
+};
+struct ShardGraph {
+    ShardKey key;
+    uint32_t uses = 0;
+    bool failed = false;
+    cudaGraphExec_t exec = nullptr;
+    Fr* tmp[1 << MAX_LOG_G] = {};
+};
+thread_local std::vector<ShardGraph> t_shard_graphs;
+
+void shard_graph_release(ShardGraph& e) {
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+    for (int q = 0; q < (1 << MAX_LOG_G); q++) {
+        if (e.tmp[q]) {
+            DeviceScope scope(e.key.dev[q]);
+            cudaFree(e.tmp[q]);
+        }
+    }
 }
 
 int32_t ntt_sharded_dev(Fr* const* blocks, const int32_t* dev_index, uint32_t log_n, uint32_t log_g, uint32_t kind) {
@@ -606,7 +680,6 @@ int32_t ntt_sharded_dev(Fr* const* blocks, const int32_t* dev_index, uint32_t lo
     }
     // every device runs log_g cross stages on a slice of m / g local offsets, so the block must hold >= g elements
     MPC_ARG_CHECK(log_n >= 2 * log_g);
-    const bool inverse = kind == MPC_CUDA_NTT_IFFT || kind == MPC_CUDA_NTT_COSET_IFFT;
     int dev[1 << MAX_LOG_G];
     cudaStream_t st[1 << MAX_LOG_G];
     bool distinct = false;
@@ -621,30 +694,67 @@ int32_t ntt_sharded_dev(Fr* const* blocks, const int32_t* dev_index, uint32_t lo
         MPC_TRY(scope.rc);
         st[q] = scope.s;
     }
-    const size_t m = (size_t)1 << (log_n - log_g), slice = m >> log_g;
-    if (inverse) {
-        for (int q = 0; q < g; q++) {
-            DeviceScope scope(dev[q]);
-            MPC_TRY(scope.rc);
-            MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_IFFT, 1, st[q]));
+    const int64_t gopt = g_opt_ntt_graph.load(std::memory_order_relaxed);
+    const bool want_graph = (gopt == 1 || (gopt == 0 && distinct)) && !g_opt_profile.load(std::memory_order_relaxed);
+    if (!want_graph) return ntt_sharded_body(blocks, dev, st, g, log_n, log_g, kind, nullptr, false);
+
+    ShardKey key;
+    memset(&key, 0, sizeof(key));
+    for (int q = 0; q < g; q++) { key.blocks[q] = blocks[q]; key.dev[q] = dev[q]; }
+    key.log_n = log_n; key.log_g = log_g; key.kind = kind;
+    ShardGraph* e = nullptr;
+    for (ShardGraph& c : t_shard_graphs)
+        if (c.key == key) e = &c;
+    if (!e) {
+        if (t_shard_graphs.size() >= 32) {           // bounded cache: drop the oldest entry
+            shard_graph_release(t_shard_graphs.front());
+            t_shard_graphs.erase(t_shard_graphs.begin());
+        }
+        t_shard_graphs.emplace_back();
+        e = &t_shard_graphs.back();
+        e->key = key;
+    }
+    e->uses++;
+    if (e->failed || e->uses == 1) return ntt_sharded_body(blocks, dev, st, g, log_n, log_g, kind, nullptr, false);
+    if (!e->exec) {
+        // capture: ping-pong buffers first (no allocation inside the graph), then the launches
+        const size_t m = (size_t)1 << (log_n - log_g);
+        bool ok = true;
+        if (log_n - log_g > (uint32_t)NTT_MAX_DEG) {
+            for (int q = 0; q < g && ok; q++) {
+                DeviceScope scope(dev[q]);
+                ok = scope.rc == MPC_CUDA_OK && cudaMalloc((void**)&e->tmp[q], m * sizeof(Fr)) == cudaSuccess;
+            }
+        }
+        cudaGraph_t graph = nullptr;
+        {
+            DeviceScope scope(dev[0]);
+            ok = ok && scope.rc == MPC_CUDA_OK && cudaStreamBeginCapture(st[0], cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        }
+        if (ok) {
+            int32_t rc = ntt_sharded_body(blocks, dev, st, g, log_n, log_g, kind, e->tmp[0] ? e->tmp : nullptr, true);
+            DeviceScope scope(dev[0]);
+            cudaError_t ce = cudaStreamEndCapture(st[0], &graph);
+            ok = rc == MPC_CUDA_OK && ce == cudaSuccess && graph != nullptr;
+            if (ok) ok = cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (!ok) {                                   // graphs are an optimisation: fall back to direct launches for good
+            cudaGetLastError();
+            e->failed = true;
+            e->exec = nullptr;
+            return ntt_sharded_body(blocks, dev, st, g, log_n, log_g, kind, nullptr, false);
         }
     }
-    MPC_TRY(cross_barrier(dev, st, g));          // every block is ready to be read by every device
-    for (int r = 0; r < g; r++) {
-        DeviceScope scope(dev[r]);
+    // the graph runs on the first stream: order it after the other streams' earlier work and them after it
+    MPC_TRY(cross_barrier(dev, st, g, BAR_JOIN));
+    {
+        DeviceScope scope(dev[0]);
         MPC_TRY(scope.rc);
-        MPC_TRY(ntt_cross_launch(blocks, 0, log_n, log_g, (size_t)r * slice, slice, kind, st[r]));
+        MPC_CUDA_TRY(cudaGraphLaunch(e->exec, st[0]));
+        count_launch();
     }
-    MPC_TRY(cross_barrier(dev, st, g));          // every block received the stores of every device
-    if (!inverse) {
-        for (int q = 0; q < g; q++) {
-            DeviceScope scope(dev[q]);
-            MPC_TRY(scope.rc);
-            MPC_TRY(ntt_dev(blocks[q], log_n - log_g, MPC_CUDA_NTT_FFT, 1, st[q]));
-        }
-        MPC_TRY(cross_barrier(dev, st, g));      // the first device's stream now orders after the whole job
-    }
-    return MPC_CUDA_OK;
+    return cross_barrier(dev, st, g, BAR_FORK);
 }
 
 // natural block order <-> the transposed order the forward kinds produce: out[r][mm] = X[mm g + bitrev(r)].
