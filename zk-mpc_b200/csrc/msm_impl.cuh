@@ -490,6 +490,9 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(cons
 #endif
 constexpr int AFF_B = MSM_AFF_B;   // pairs per lane per shared inversion (prefix products: AFF_B field elements of local memory)
 constexpr int AFF_THREADS = 128;
+#ifndef AFF_MIN_BLOCKS
+#define AFF_MIN_BLOCKS 3
+#endif
 
 template <class F>
 DEV bool aff_none(const Affine<F>& p) { return p.x.is_zero() && p.y.is_zero(); }
@@ -557,7 +560,7 @@ DEV int aff_load_pair(const Affine<F>* __restrict__ pts, const uint32_t* __restr
 // `batch` (<= AFF_B) pairs per lane share one inversion: long batches amortise it, short ones keep every warp of
 // the machine busy on small inputs (chosen by the host from the pair count)
 template <class F, bool GATHER>
-__global__ void __launch_bounds__(AFF_THREADS) k_affine_pairs(const Affine<F>* __restrict__ pts,
+__global__ void __launch_bounds__(AFF_THREADS, sizeof(F) > 48 ? 1 : AFF_MIN_BLOCKS) k_affine_pairs(const Affine<F>* __restrict__ pts,
                                                               const uint32_t* __restrict__ idx, size_t npairs,
                                                               Affine<F>* __restrict__ out, int batch) {
     const uint32_t lane = threadIdx.x & 31;
