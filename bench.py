@@ -150,6 +150,17 @@ def workload_name(log_n):
     return "share MSM G1, 2^%d points per GPU, uniform share scalars" % log_n
 
 
+def shared_config(log_n, world, ref_log_n):
+    """the `config` object both arms print, key for key: the workload, and the statement that the CPU arm (and the
+    cpu_baseline leg) times a bounded sample of it"""
+    n = 1 << log_n
+    return {"workload": workload_name(log_n), "points_per_gpu": n, "total_points": world * n,
+            "l2": "GPU arm: the inputs of a step (%.1f GB of bases + scalars per GPU, or the %d-window table) exceed the "
+                  "126 MB L2, so no flush between timed iterations" % (n * 128 / 1e9, 12),
+            "cpu_arm_sample": "the CPU restatement is timed on the first 2^%d points of this workload (a full 2^%d MSM "
+                              "takes ~25 s per step on 16 cores)" % (min(ref_log_n, log_n), log_n)}
+
+
 # ======================================================================================= reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -182,7 +193,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 limbs (Montgomery Fq/Fr)", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_n), "sample_points": n},
+        "config": shared_config(args.log_n, max(args.gpus, 1), args.ref_log_n),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -621,14 +632,13 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (Montgomery Fq 12x32 / Fr 8x32)", "data": "synthetic",
-            "config": {"workload": workload_name(log_n), "points_per_gpu": n, "total_points": world * n,
-                       "crs": "registered on the device" + ("" if args.no_table else
-                                                            " with its window table 2^(%d w) P_i, w < %d (one bucket set; "
-                                                            "build time and size in extra.table)" % (table["window_bits"], table["windows"])),
-                       "sharding": "point range + NCCL all-gather of Jacobian partials",
-                       "cpu_baseline_sample": "first 2^%d points of the same inputs" % min(args.ref_log_n, log_n),
-                       "l2": "inputs (%.1f GB of bases + scalars, %.1f GB of sort scratch) exceed the 126 MB L2" % (
-                           n * 128 / 1e9, n * 16 * 8 / 1e9)},
+            "config": shared_config(log_n, world, args.ref_log_n),
+            "setup": {"crs": "registered on the device" + ("" if args.no_table else
+                                                          " with its window table 2^(%d w) P_i, w < %d (one bucket set; "
+                                                          "build time and size in extra.table)" % (table["window_bits"], table["windows"])),
+                      "sharding": "point range + NCCL all-gather of Jacobian partials",
+                      "l2": "inputs (%.1f GB of bases + scalars, %.1f GB of sort scratch) exceed the 126 MB L2" % (
+                          n * 128 / 1e9, n * 16 * 8 / 1e9)},
             "stage_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clock_info, "extra": extra,
         }
@@ -842,8 +852,7 @@ def bench_strong(pkg, H, S, L, world, log_n, bases_host, scalars_host, args):
                                 "speedup": (single / tf) if single else None,
                                 "efficiency": (single / tf / world) if single else None,
                                 "nvlink_bytes_per_gpu": 2 * (world - 1) * (m // world) * 32,
-                                "timing": "host clock around 5 back-to-back asynchronous transforms + one stream sync; repeated transforms "
-                                          "of the same blocks replay a CUDA graph captured across the devices' streams"}
+                                "timing": "host clock around 5 back-to-back asynchronous transforms + one stream sync"}
     return out
 
 

@@ -55,9 +55,8 @@ int32_t mpc_cuda_device_count(void);
  *   "msm_host_chunks"  point-range chunks a host-buffer MSM is streamed in (copy/compute overlap), 1..16
  *   "ntt_occupancy"    NTT pass kernels built for one more resident CTA per SM (64 registers): 0 = automatic (the
  *                      256-row tile shape only), 1 = every shape, 2 = none
- *   "ntt_graph"        replay of repeated sharded transforms (same blocks, size, kind) from a CUDA graph captured
- *                      across the devices' streams: 0 = automatic (when the blocks sit on different devices), 1 = always,
- *                      2 = never
+ *   "ntt_graph"        1: replay repeated sharded transforms (same blocks, size, kind) from a CUDA graph captured
+ *                      across the devices' streams (off by default: measured no faster than direct launches)
  *   "ntt_generic"      1: run every NTT pass through the generic (runtime tile shape) kernel instead of the
  *                      compile-time-shaped ones (A/B measurements; results are identical)
  *   "profile"          1: bracket pipeline stages with CUDA events on the launching stream */

@@ -26,7 +26,7 @@ using namespace mpc;
 namespace mpc {
 std::atomic<int64_t> g_opt_ntt_occupancy{0};    // 1: the pass kernels compiled for one more CTA per SM
 std::atomic<int64_t> g_opt_ntt_generic{0};
-std::atomic<int64_t> g_opt_ntt_graph{0};        // sharded NTT replay through CUDA graphs: 0 auto, 1 always, 2 never      // 1: always run the generic pass kernel (A/B measurements, tests)
+std::atomic<int64_t> g_opt_ntt_graph{0};        // sharded NTT replay through CUDA graphs: 1 = on (0 / 2 = off)      // 1: always run the generic pass kernel (A/B measurements, tests)
 }
 
 namespace {
@@ -641,10 +641,11 @@ int32_t ntt_sharded_body(Fr* const* blocks, const int* dev, cudaStream_t* st, in
 }
 
 // A sharded transform is ~170 driver calls from one host thread (8 devices x (cross stage + 3 passes) + the event
-// barriers), about as long as the GPU work itself at 2^24 over 8 GPUs.  Repeated transforms of the same blocks
-// (witness_map runs seven per proof over the same buffers) are therefore replayed from a CUDA graph captured across
-// the devices' streams: first call direct (builds tables, sets attributes), second call captured, later calls one
-// cudaGraphLaunch between two small real barriers that order it against the other streams' earlier / later work.
+// barriers).  Repeated transforms of the same blocks (witness_map runs seven per proof over the same buffers) can
+// be replayed from a CUDA graph captured across the devices' streams (option ntt_graph = 1): first call direct
+// (builds tables, sets attributes), second call captured, later calls one cudaGraphLaunch between two small real
+// barriers that order it against the other streams' earlier / later work.  Off by default: on 8 B200s the replay
+// (0.680 ms at 2^24) is no faster than the direct launches (0.686 ms) — the GPUs, not the host, are the limit.
 struct ShardKey {
     Fr* blocks[1 << MAX_LOG_G];
     int dev[1 << MAX_LOG_G];
@@ -695,7 +696,10 @@ int32_t ntt_sharded_dev(Fr* const* blocks, const int32_t* dev_index, uint32_t lo
         st[q] = scope.s;
     }
     const int64_t gopt = g_opt_ntt_graph.load(std::memory_order_relaxed);
-    const bool want_graph = (gopt == 1 || (gopt == 0 && distinct)) && !g_opt_profile.load(std::memory_order_relaxed);
+    // measured on 2 and 8 B200s (tools/bench_sharded_ntt.py): direct launches and graph replay take the same time (the
+    // transform is bound by the GPUs, not by the ~170 driver calls), so replay is opt-in
+    const bool want_graph = gopt == 1 && !g_opt_profile.load(std::memory_order_relaxed);
+    (void)distinct;
     if (!want_graph) return ntt_sharded_body(blocks, dev, st, g, log_n, log_g, kind, nullptr, false);
 
     ShardKey key;
