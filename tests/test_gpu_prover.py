@@ -290,3 +290,106 @@ def test_groth16_prove_sequence_three_parties(H, orc, pkg, shape, zk):
         assert _same(acc, exp[key]), key
     state["pk"].release()
     state["r1cs"].release()
+
+
+# ----------------------------------------------------------------------------- Marlin-side compositions (a16)
+class _SeqNet:
+    """three parties played one after the other: exchange() replays payloads recorded in a first pass"""
+
+    def __init__(self, party, store):
+        self.party, self.n_parties, self.store, self.k = party, 3, store, 0
+
+    def exchange(self, payload):
+        slot = self.store.setdefault(self.k, {})
+        slot[self.party] = payload
+        self.k += 1
+        if len(slot) < 3:
+            raise _NeedOthers()
+        return [slot[p] for p in range(3)]
+
+
+class _NeedOthers(Exception):
+    pass
+
+
+def _shares_of(orc, pkg, seed, opened, parties=3):
+    sh = [pkg.synth.fr_uniform(seed + p, len(opened)) for p in range(parties)]
+    sh[0] = orc.vec_op("sub", opened, orc.open_sum(np.stack(sh[1:])))
+    return sh
+
+
+def _sum_points(orc, pts):
+    acc = pts[0]
+    for q in pts[1:]:
+        acc = orc.g1_add(acc[0], q[0], acc[1], q[1])
+    return acc
+
+
+def test_kzg_commit_and_open_on_shares(H, orc, pkg):
+    """KZG10::commit / open (poly-commit/src/kzg10/mod.rs:140-290) with shared coefficients, a shared blinding
+    polynomial and a public point: the sum of the parties' results equals the plain computation on the oracle"""
+    K, S = pkg.kzg, pkg.synth
+    deg = 1500
+    pg, pgg = orc.g1_generate(0xD10, deg + 1), orc.g1_generate(0xD11, 8)
+    powers = K.Powers(pg, pgg)
+    p_open, blind_open = S.fr_uniform(0xD20, deg + 1), S.fr_uniform(0xD21, 4)
+    z = S.fr_uniform(0xD22, 1)[0]
+    p_sh, b_sh = _shares_of(orc, pkg, 0xD30, p_open), _shares_of(orc, pkg, 0xD40, blind_open)
+    # commit
+    got = _sum_points(orc, [K.commit(powers, p_sh[i], b_sh[i]) for i in range(3)])
+    c, rc = orc.g1_msm(pg, p_open, threads=8), orc.g1_msm(pgg[:4], blind_open)
+    assert _same(got, orc.g1_add(c[0], rc[0], c[1], rc[1]))
+    assert _same(_sum_points(orc, [K.commit(powers, p_sh[i]) for i in range(3)]), c)
+    # open
+    one = S.FR_R_LIMBS
+    den = np.stack([orc.fr("neg", z[None])[0], one])
+    wit, _ = orc.poly_div(p_open, den)
+    rwit, _ = orc.poly_div(blind_open, den)
+    w = orc.g1_msm(pg[:len(wit)], wit, threads=8)
+    rw = orc.g1_msm(pgg[:len(rwit)], rwit)
+    exp_w = orc.g1_add(w[0], rw[0], w[1], rw[1])
+    res = [K.open(powers, p_sh[i], z, b_sh[i]) for i in range(3)]
+    assert _same(_sum_points(orc, [r[0] for r in res]), exp_w)
+    assert np.array_equal(orc.open_sum(np.stack([r[1][None] for r in res]))[0], orc.horner(blind_open, z))
+    assert _same(_sum_points(orc, [K.open(powers, p_sh[i], z)[0] for i in range(3)]), w)
+    powers.release()
+
+
+def test_dense_polynomial_mul_on_shares(H, orc, pkg):
+    """DensePolynomial::mul (dense.rs:567-583): public x shared is local; shared x shared is a Beaver batch product
+    on the evaluations (two opens).  Lengths chosen so the domain is not tight (300 + 211 -> 512)."""
+    K, S = pkg.kzg, pkg.synth
+    a_open, b_open = S.fr_uniform(0xE10, 300), S.fr_uniform(0xE11, 211)
+    n = 512
+
+    def plain(a, b):
+        pa, pb = np.zeros((n, 4), dtype=np.uint64), np.zeros((n, 4), dtype=np.uint64)
+        pa[:len(a)], pb[:len(b)] = a, b
+        return orc.ntt(orc.vec_op("mul", orc.ntt(pa, "fft"), orc.ntt(pb, "fft")), "ifft")
+
+    exp = plain(a_open, b_open)
+    assert not exp[510:].any()                                   # degree 509: the top coefficients are zero
+    b_sh = _shares_of(orc, pkg, 0xE20, b_open)
+    got = orc.open_sum(np.stack([K.poly_mul_public(a_open, b_sh[i]) for i in range(3)]))
+    assert np.array_equal(got, exp)
+    # shared x shared with a random (consistent) triple
+    a_sh = _shares_of(orc, pkg, 0xE30, a_open)
+    tx_o, ty_o = S.fr_uniform(0xE40, n), S.fr_uniform(0xE41, n)
+    tz_o = orc.vec_op("mul", tx_o, ty_o)
+    tx, ty, tz = (_shares_of(orc, pkg, 0xE50 + 8 * k, v) for k, v in enumerate((tx_o, ty_o, tz_o)))
+    store, outs = {}, [None] * 3
+    for rnd in range(3):                                         # each pass gets one exchange further
+        for i in range(3):
+            try:
+                outs[i] = K.poly_mul_shared(a_sh[i], b_sh[i], _SeqNet(i, store), (tx[i], ty[i], tz[i]))
+            except _NeedOthers:
+                pass
+    assert all(o is not None for o in outs)
+    assert np.array_equal(orc.open_sum(np.stack(outs)), exp)
+    # LC accumulation (dense.rs:345-372): acc += (f, other) with ragged lengths
+    f = S.fr_uniform(0xE60, 1)[0]
+    acc = K.add_assign_scaled(a_open, f, b_open[:100])
+    exp_acc = a_open.copy()
+    exp_acc[:100] = orc.vec_op("axpy", a_open[:100], b_open[:100], c=f)
+    assert np.array_equal(acc, exp_acc)
+    assert len(K.add_assign_scaled(b_open[:10], f, a_open)) == 300

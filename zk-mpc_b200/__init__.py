@@ -14,3 +14,4 @@ from . import host  # noqa: F401
 from . import sharding  # noqa: F401
 from . import wire  # noqa: F401
 from . import groth16  # noqa: F401
+from . import kzg  # noqa: F401
