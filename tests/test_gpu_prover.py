@@ -393,3 +393,58 @@ def test_dense_polynomial_mul_on_shares(H, orc, pkg):
     exp_acc[:100] = orc.vec_op("axpy", a_open[:100], b_open[:100], c=f)
     assert np.array_equal(acc, exp_acc)
     assert len(K.add_assign_scaled(b_open[:10], f, a_open)) == 300
+
+
+def test_groth16_prove_sequence_spdz(H, orc, pkg):
+    """the malicious backend (BASELINE config 5): [sh | mac] planes, MAC key 1 shared as (1, 0, 0), both opens MAC
+    checked; the opened proof equals the plain prover's, the mac components repeat the sh ones (spdz.rs:482-488), and
+    a corrupted MAC plane is caught by the check"""
+    G, S = pkg.groth16, pkg.synth
+    nc, ni, nv, parties = 200, 3, 230, 3
+    mats = helpers.synth_r1cs(pkg, 0xF10, nc, nv)
+    log_n = max(nc + ni - 1, 0).bit_length()
+    pkarr = helpers.synth_proving_key(orc, 0xF20, nv, ni, 1 << log_n)
+    z_open = S.fr_uniform(0xF30, nv)
+    z_open[0] = S.FR_R_LIMBS
+    sh = S.additive_shares(0xF40, z_open, parties, ni, lambda a, b: orc.vec_op("sub", a, b))
+    mac = S.additive_shares(0xF50, z_open, parties, ni, lambda a, b: orc.vec_op("sub", a, b))     # key 1: macs open to z too
+    zero = np.zeros(4, dtype=np.uint64)
+
+    def run(mac_planes):
+        nets = helpers.ThreadNet.make(parties)
+        ready = threading.Barrier(parties)
+        state = {}
+
+        def party(p):
+            H.set_party(p, parties)
+            H.set_device(0)
+            if p == 0:
+                state["pk"] = G.ProvingKey(**pkarr)
+                state["r1cs"] = G.R1CS(*mats, num_inputs=ni, num_vars=nv)
+            ready.wait()
+            sess = G.ProverSession(state["pk"], state["r1cs"])
+            try:
+                return sess.prove(np.stack([sh[p], mac_planes[p]]), nets[p], spdz=True)
+            except H.MpcCudaError as e:
+                return e
+            finally:
+                sess.close()
+
+        out = _run_parties(party, parties)
+        H.set_party(0, 3)
+        state["pk"].release()
+        state["r1cs"].release()
+        return out
+
+    proofs = run(mac)
+    exp = helpers.oracle_groth16(orc, pkarr, mats, ni, z_open, log_n, zero, zero)
+    for key, add in (("a", orc.g1_add), ("b", orc.g2_add), ("c", orc.g1_add)):
+        acc = proofs[0][key]
+        for q in proofs[1:]:
+            acc = add(acc[0], q[key][0], acc[1], q[key][1])
+        assert _same(acc, exp[key]), key
+        assert all(_same(pr["mac"][key], pr[key]) for pr in proofs)
+    bad = [m.copy() for m in mac]
+    bad[1][ni + 7, 0] ^= np.uint64(1)                       # one party's MAC share of one witness value is off
+    res = run(bad)
+    assert all(isinstance(r, H.MpcCudaError) and "MAC check" in str(r) for r in res)

@@ -68,6 +68,31 @@ HD void xyzz_dbl(XYZZ<F>& p) {
     p.zzz = mul(w, p.zzz);
 }
 
+// The same addition with every product inlined (mul_fast): the hot loop of the bucket accumulation.  For G2 the
+// out-of-line Fq2 products of xyzz_madd pass their operands through local memory on every call.
+template <class F>
+HD void xyzz_madd_fast(XYZZ<F>& p, const F& qx, const F& qy) {
+    if (p.is_inf()) {
+        p.x = qx; p.y = qy; p.zz = F::one(); p.zzz = F::one();
+        return;
+    }
+    F pp = sub(mul_fast(qx, p.zz), p.x);
+    F r = sub(mul_fast(qy, p.zzz), p.y);
+    if (pp.is_zero()) {
+        if (r.is_zero()) xyzz_mdbl(p, qx, qy);      // rare: the out-of-line tangent
+        else p = XYZZ<F>::infinity();
+        return;
+    }
+    F p2 = sqr_fast(pp);
+    F p3 = mul_fast(pp, p2);
+    F q = mul_fast(p.x, p2);
+    F x3 = sub(sub(sqr_fast(r), p3), dbl(q));
+    p.y = sub(mul_fast(r, sub(q, x3)), mul_fast(p.y, p3));
+    p.x = x3;
+    p.zz = mul_fast(p.zz, p2);
+    p.zzz = mul_fast(p.zzz, p3);
+}
+
 // p += (qx, qy), the affine point being finite
 template <class F>
 HD void xyzz_madd(XYZZ<F>& p, const F& qx, const F& qy) {

@@ -30,8 +30,10 @@ template <class P> HD Fp2<P> neg(const Fp2<P>& a) { Fp2<P> r; r.c0 = neg(a.c0); 
 template <class P> HD Fp<P> mul5(const Fp<P>& a) { return add(dbl(dbl(a)), a); }
 
 // Karatsuba: (a0 + a1 u)(b0 + b1 u) = (a0 b0 - 5 a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u
+// mul_fast / sqr_fast are the inlined bodies (the bucket-accumulation kernel: operands stay in registers);
+// mul / sqr are the out-of-line versions every other G2 kernel calls (compile time, see ptx.cuh).
 template <class P>
-HD_NOINLINE Fp2<P> mul(const Fp2<P>& a, const Fp2<P>& b) {
+HD Fp2<P> mul_fast(const Fp2<P>& a, const Fp2<P>& b) {
     Fp<P> v0 = mul(a.c0, b.c0);
     Fp<P> v1 = mul(a.c1, b.c1);
     Fp<P> s = mul(add(a.c0, a.c1), add(b.c0, b.c1));
@@ -40,10 +42,12 @@ HD_NOINLINE Fp2<P> mul(const Fp2<P>& a, const Fp2<P>& b) {
     r.c0 = sub(v0, mul5(v1));
     return r;
 }
+template <class P>
+HD_NOINLINE Fp2<P> mul(const Fp2<P>& a, const Fp2<P>& b) { return mul_fast(a, b); }
 
 // complex squaring: c1 = 2 a0 a1, c0 = (a0 + a1)(a0 - 5 a1) + 4 a0 a1
 template <class P>
-HD_NOINLINE Fp2<P> sqr(const Fp2<P>& a) {
+HD Fp2<P> sqr_fast(const Fp2<P>& a) {
     Fp<P> v = mul(a.c0, a.c1);
     Fp<P> t = mul(add(a.c0, a.c1), sub(a.c0, mul5(a.c1)));
     Fp2<P> r;
@@ -51,6 +55,12 @@ HD_NOINLINE Fp2<P> sqr(const Fp2<P>& a) {
     r.c0 = add(t, dbl(r.c1));
     return r;
 }
+template <class P>
+HD_NOINLINE Fp2<P> sqr(const Fp2<P>& a) { return sqr_fast(a); }
+
+// base field: the inlined product is the only one
+template <class P> HD Fp<P> mul_fast(const Fp<P>& a, const Fp<P>& b) { return mul(a, b); }
+template <class P> HD Fp<P> sqr_fast(const Fp<P>& a) { return sqr(a); }
 
 // 1 / (a0 + a1 u) = (a0 - a1 u) / (a0^2 + 5 a1^2); 0 -> 0
 template <class P>

@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(1024) k_build_tasks(const uint32_t* __restrict
 // DENSE: the tasks run over an array of pre-reduced affine points (k_affine_pairs) instead of an index list into
 // the bases: sequential 96-byte reads, entries (0, 0) are holes.
 template <class F, bool DENSE>
-__global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(const Affine<F>* __restrict__ bases,
+__global__ void __launch_bounds__(ACC_THREADS, sizeof(F) > 48 ? 2 : ACC_MIN_BLOCKS) k_accumulate(const Affine<F>* __restrict__ bases,
                                                             const uint32_t* __restrict__ sorted, size_t n, uint32_t nb,
                                                             const uint4* __restrict__ tasks,
                                                             uint32_t* __restrict__ counters,
@@ -462,13 +462,13 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_accumulate(cons
             Affine<F> p = load_pod_ro(bases + first + k);
             k++;
             if (p.x.is_zero() && p.y.is_zero()) continue;
-            xyzz_madd(acc, p.x, p.y);
+            xyzz_madd_fast(acc, p.x, p.y);
         } else {
             uint32_t e = __ldg(sorted + first + k);
             k++;
             Affine<F> p = load_pod_ro(bases + (e & ~msm::DIGIT_NEG));
             if (e & msm::DIGIT_NEG) p.y = neg(p.y);
-            xyzz_madd(acc, p.x, p.y);
+            xyzz_madd_fast(acc, p.x, p.y);
         }
     }
 }

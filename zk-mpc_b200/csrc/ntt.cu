@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS,
             uint32_t d = (j << a.s0) + (tile << lc) + cc;
             // back to the canonical range: a strict product does it (input < 2p), else two conditional subtractions
             if (a.scale) x = mul(x, load_fe_ro(a.scale));
-            else x = reduce_full(x);
+            else if (!a.post_lo) x = reduce_full(x);
             if (a.post_lo) {
                 x = mul(x, load_fe_ro(a.post_lo + (d & ((1u << COSET_LO_BITS) - 1))));
                 if (a.log_n > COSET_LO_BITS) x = mul(x, load_fe_ro(a.post_hi + (d >> COSET_LO_BITS)));
@@ -296,6 +296,7 @@ struct DomainCache {
     Fr* tw[MAX_LOG_N + 1] = {};            // forward twiddle tables by domain log-size
     Fr *g_lo = nullptr, *gi_lo = nullptr;  // 22^i, 22^-i, i < 4096
     Fr *g_hi = nullptr, *gi_hi = nullptr;  // 22^(±4096 h), h < 2^hi_bits
+    Fr* gi_lo_scaled[MAX_LOG_N + 1] = {};  // n^-1 * 22^-i, i < 4096, per domain size: coset_ifft folds its 1/n here
     Fr* gen_pair = nullptr;                // [22, 22⁻¹]
     uint32_t hi_bits = 0;
 };
@@ -350,6 +351,15 @@ int32_t ensure_tables(int dev_index, uint32_t log_n, bool coset, cudaStream_t s,
             MPC_CUDA_TRY(cudaStreamSynchronize(s));
             d.g_lo = a;
             d.gi_lo = b;
+        }
+        if (log_n >= 1 && !d.gi_lo_scaled[log_n]) {
+            Fr* a = nullptr;
+            MPC_CUDA_TRY(cudaMalloc((void**)&a, lo_n * sizeof(Fr)));
+            MPC_CUDA_TRY(cudaMemcpyAsync(a, d.gi_lo, lo_n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+            k_mul_const_dev<<<(unsigned)(lo_n / 256), 256, 0, s>>>(a, d.consts + 48 + log_n, lo_n);
+            MPC_KERNEL_CHECK();
+            MPC_CUDA_TRY(cudaStreamSynchronize(s));
+            d.gi_lo_scaled[log_n] = a;
         }
         uint32_t need = log_n > COSET_LO_BITS ? log_n - COSET_LO_BITS : 0;
         if (need && (!d.g_hi || need > d.hi_bits)) {
@@ -417,8 +427,8 @@ int32_t ntt_dev(Fr* data, uint32_t log_n, uint32_t kind, uint32_t batch, cudaStr
             tiles = ((size_t)1 << s0) >> a.lc;
         }
         if (first && kind == MPC_CUDA_NTT_COSET_FFT) { a.pre_lo = d->g_lo; a.pre_hi = d->g_hi; }
-        if (last && inverse) a.scale = d->consts + 48 + log_n;
-        if (last && kind == MPC_CUDA_NTT_COSET_IFFT) { a.post_lo = d->gi_lo; a.post_hi = d->gi_hi; }
+        if (last && kind == MPC_CUDA_NTT_IFFT) a.scale = d->consts + 48 + log_n;
+        if (last && kind == MPC_CUDA_NTT_COSET_IFFT) { a.post_lo = d->gi_lo_scaled[log_n]; a.post_hi = d->gi_hi; }   // 1/n folded in
         uint32_t E = (1u << deg) << a.lc;
         MPC_ARG_CHECK(tiles < ((size_t)1 << 31) && batch < 65536);
         dim3 grid((unsigned)tiles, batch);

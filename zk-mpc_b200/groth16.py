@@ -126,30 +126,56 @@ class ProverSession:
         for b in [self.za, self.zb, self.lh] + self.parts:
             b.free()
 
-    def prove(self, assignment, net, triple=None, r=None, s=None):
+    def prove(self, assignment, net, triple=None, r=None, s=None, spdz=False):
         """One party's share of the proof (a, b, c) from its share of the full assignment (instance | witness
         values, (num_vars, 4) Montgomery limbs; the constant 1 and public inputs already lifted with from_public).
 
         net: .party, .n_parties, .exchange(uint8 array) -> list of every party's array in party order (a
         broadcast).  Returns {"a": (xy, inf), "b": (xy, inf) over G2, "c": (xy, inf)}: the shares
-        MpcPairingEngine would reveal."""
+        MpcPairingEngine would reveal.
+
+        spdz (the malicious backend, mpc-algebra/src/share/spdz.rs): assignment and triple are (2, ., 4) = [sh, mac]
+        planes; the witness map runs on both planes, each of the two opens is followed by its MAC check (the local
+        halves dx = mac_share * val - mac are exchanged and must sum to zero, spdz.rs:177-196), and — the reference's
+        own quirk — every MSM reads the sh plane for BOTH components (spdz.rs:482-488), so the mac component of each
+        proof element equals its sh component: returned under "mac"."""
         pk, r1cs = self.pk, self.r1cs
         leader = net.party == 0
-        z = np.ascontiguousarray(assignment, dtype=np.uint64).reshape(-1, 4)
+        if spdz:
+            planes = np.ascontiguousarray(assignment, dtype=np.uint64)
+            if planes.ndim != 3 or planes.shape[0] != 2:
+                raise ValueError("SPDZ assignments are (2, num_vars, 4) = [sh, mac] planes")
+            z = planes[0]
+        else:
+            z = np.ascontiguousarray(assignment, dtype=np.uint64).reshape(-1, 4)
         if z.shape[0] != r1cs.num_vars:
             raise ValueError("assignment has %d values, the circuit %d variables" % (z.shape[0], r1cs.num_vars))
         n = r1cs.n
-        tx, ty, tz = triple if triple is not None else dummy_triple(n, leader)
+        if triple is not None:
+            tx, ty, tz = triple
+        else:
+            tx, ty, tz = dummy_triple(n, leader)
+            if spdz:                                # MAC key 1 shared as (1, 0, 0): mac plane = sh plane
+                tx, ty, tz = (np.stack([v, v]) for v in (tx, ty, tz))
         zero, one = np.zeros(4, dtype=np.uint64), FR_R_LIMBS
         r = zero if r is None else np.asarray(r, dtype=np.uint64)
         s = zero if s is None else np.asarray(s, dtype=np.uint64)
 
         # ---- witness map: the vectors stay on the device; only wire payloads cross PCIe for the two opens
-        ma, mb, st = H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, z, r1cs.num_inputs, r1cs.log_n, tx, ty)
+        ma, mb, st = H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, planes if spdz else z, r1cs.num_inputs, r1cs.log_n,
+                                              tx, ty, spdz=spdz)
         try:
-            sx = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(ma))), n)
-            oy = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(mb))), n)
-            h_ptr = H.witness_map_finish_dev(st, tz, sx, oy, leader)
+            def open_masked(masked):
+                val = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(masked[0] if spdz else masked))), n)
+                if spdz:                            # batch_open's MAC check, local half + zero test of the sum
+                    dx = H.spdz_mac_check(val, masked[1], leader)
+                    if H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(dx))), n).any():
+                        raise H.MpcCudaError("SPDZ MAC check failed on an opened value")
+                return val
+
+            sx = open_masked(ma)
+            oy = open_masked(mb)
+            h_ptr = H.witness_map_finish_dev(st, tz, sx, oy, leader)        # SPDZ: [sh | mac] planes, sh first
 
             # ---- scalars of the four MSMs, resident: [assignment[1:] | 1 | 1 | r or s] (leader) and [witness | h]
             tail_a = np.stack([one, one, r]) if leader else np.zeros((3, 4), dtype=np.uint64)
@@ -185,7 +211,10 @@ class ProverSession:
             pts = np.stack([g_a[0], g1_b[0], pk.delta_g1, lh_acc[0]])
             inf = np.array([g_a[1], g1_b[1], 0, lh_acc[1]], dtype=np.uint8)
             g_c = H.msm_g1(pts, np.stack([s, r, rs, one]), inf=inf)
-        return {"a": g_a, "b": g2_b, "c": g_c}
+        out = {"a": g_a, "b": g2_b, "c": g_c}
+        if spdz:
+            out["mac"] = {"a": g_a, "b": g2_b, "c": g_c}
+        return out
 
 
 def prove_party(pk, r1cs, assignment, net, triple=None, r=None, s=None):
