@@ -52,6 +52,9 @@ int32_t mpc_cuda_device_count(void);
  *   "msm_task_len"     maximum points one accumulation task adds (bucket splitting)
  *   "msm_affine"       batched-affine pre-reduction of the bucket lists before the XYZZ accumulation: 0 = automatic
  *                      (two rounds when buckets hold >= 8 entries on average), 1 = off, 2 = one round, 3 = two rounds
+ *   "msm_affine_split" the pre-reduction as two kernels pipelined over two streams (the memory-bound product pass of
+ *                      segment j+1 under the multiplier-bound addition pass of segment j): 0 or 2 = one fused
+ *                      kernel (default: the split measured 7% slower at 2^24), 1 = split
  *   "msm_host_chunks"  point-range chunks a host-buffer MSM is streamed in (copy/compute overlap), 1..16
  *   "ntt_occupancy"    NTT pass kernels built for one more resident CTA per SM (64 registers): 0 = automatic (the
  *                      256-row tile shape only), 1 = every shape, 2 = none

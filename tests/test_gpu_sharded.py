@@ -25,7 +25,7 @@ def H(pkg):
 @pytest.fixture(autouse=True)
 def _reset_options(H):
     yield
-    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks", "msm_affine", "ntt_graph"):
+    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks", "msm_affine", "msm_affine_split", "ntt_graph"):
         H.set_option(name, 0)
 
 
@@ -338,12 +338,14 @@ def test_sharded_ntt_and_msm_on_real_devices(H, orc, pkg, bases8k, log_g):
 
 
 # ----------------------------------------------------------------------------- batched-affine pre-reduction
+@pytest.mark.parametrize("split", [2, 1])                # option msm_affine_split: 2 = fused kernel, 1 = two kernels / two streams
 @pytest.mark.parametrize("rounds_opt", [2, 3])          # option msm_affine: 2 = one round, 3 = two rounds
-def test_g1_affine_prereduction_matches_oracle(H, orc, pkg, bases8k, rounds_opt):
+def test_g1_affine_prereduction_matches_oracle(H, orc, pkg, bases8k, rounds_opt, split):
     """k_affine_pairs (pairwise affine additions with one shared inversion per warp) in front of the XYZZ
     accumulation: forced on for small inputs, every window width class, duplicates (tangent), P + (-P) (infinity),
     infinity bases, skewed scalars (one huge bucket), table mode, chunked streaming"""
     H.set_option("msm_affine", rounds_opt)
+    H.set_option("msm_affine_split", split)
     try:
         n = 8000
         for seed, sc in ((1, pkg.synth.fr_uniform(0x3A0, n)), (2, pkg.synth.fr_witness_like(0x3B0, n))):
@@ -379,6 +381,7 @@ def test_g1_affine_prereduction_matches_oracle(H, orc, pkg, bases8k, rounds_opt)
         assert _same(H.msm_g1(bases8k[:n], sc[:n]), orc.g1_msm(bases8k[:n], sc[:n], threads=8))
     finally:
         H.set_option("msm_affine", 0)
+        H.set_option("msm_affine_split", 0)
 
 
 def test_g2_affine_prereduction_matches_oracle(H, orc, pkg):
@@ -387,11 +390,14 @@ def test_g2_affine_prereduction_matches_oracle(H, orc, pkg):
     bases[1:5] = bases[0]
     H.set_option("msm_affine", 3)
     try:
-        for sc in (pkg.synth.fr_uniform(0x3F0, 500), pkg.synth.fr_witness_like(0x3F1, 500)):
-            sc[1:5] = sc[0]
-            assert _same(H.msm_g2(bases, sc), orc.g2_msm(bases, sc, threads=8))
+        for split in (2, 1):
+            H.set_option("msm_affine_split", split)
+            for sc in (pkg.synth.fr_uniform(0x3F0, 500), pkg.synth.fr_witness_like(0x3F1, 500)):
+                sc[1:5] = sc[0]
+                assert _same(H.msm_g2(bases, sc), orc.g2_msm(bases, sc, threads=8))
     finally:
         H.set_option("msm_affine", 0)
+        H.set_option("msm_affine_split", 0)
 
 
 def test_g1_affine_prereduction_full_size_exact(H, orc, pkg):

@@ -19,8 +19,9 @@ for log_n in [int(x) for x in sys.argv[1:]] or [18, 20, 22, 24]:
         if table:
             h.precompute(0)
         ref = None
-        for mode, name in ((1, "off"), (2, "one_round"), (3, "two_rounds"), (0, "auto")):
+        for mode, name, split in ((1, "off", 0), (2, "one_round", 0), (3, "two_rounds", 0), (3, "two_rounds_split", 1), (0, "auto", 0)):
             H.set_option("msm_affine", mode)
+            H.set_option("msm_affine_split", split)
             H.set_option("profile", 1)
             for it in range(4):
                 L.call("mpc_cuda_msm_g1_handle_dev", C.c_uint64(h.handle), C.c_size_t(0), sc.u64(), C.c_size_t(n), out.u64(), None)
@@ -33,5 +34,6 @@ for log_n in [int(x) for x in sys.argv[1:]] or [18, 20, 22, 24]:
             H.set_option("profile", 0)
             print(json.dumps({"log_n": log_n, "table": table, "affine": name, "same_result": bool(np.array_equal(res[0], ref[0])), **st}), flush=True)
         H.set_option("msm_affine", 0)
+        H.set_option("msm_affine_split", 0)
         h.release()
     dev.free(); sc.free(); out.free()

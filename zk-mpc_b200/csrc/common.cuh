@@ -62,6 +62,7 @@ int32_t enter(cudaStream_t* stream_out);
 const DeviceInfo* current_device_info();
 int current_device_index();      // index into the init list (per-device caches are keyed by it)
 int device_list_size();          // devices of the init list (0 before init)
+int32_t aux_stream(cudaStream_t* out);   // the calling thread's second stream on its current device
 bool is_leader();
 
 // Multi-GPU entry points drive several devices from one host thread: a DeviceScope makes device `index`
@@ -98,6 +99,7 @@ extern std::atomic<int64_t> g_opt_msm_window_bits;
 extern std::atomic<int64_t> g_opt_msm_task_len;
 extern std::atomic<int64_t> g_opt_msm_host_chunks;
 extern std::atomic<int64_t> g_opt_msm_affine;
+extern std::atomic<int64_t> g_opt_msm_affine_split;
 extern std::atomic<int64_t> g_opt_profile;
 extern std::atomic<int64_t> g_opt_ntt_generic;
 extern std::atomic<int64_t> g_opt_ntt_occupancy;

@@ -28,6 +28,7 @@ static bool g_inited = false;
 static thread_local int t_dev_index = -1;       // index into g_devices
 static thread_local uint32_t t_party = 0, t_parties = 1;
 static thread_local cudaStream_t t_streams[64] = {};
+static thread_local cudaStream_t t_aux_streams[64] = {};     // second per-thread stream (producer side of pipelines)
 
 // Builds the device list in a local vector and publishes it only when every device passed, so a failed
 // attempt leaves nothing behind.  Once initialised, a request for a DIFFERENT explicit list is an error
@@ -107,6 +108,14 @@ int32_t enter(cudaStream_t* stream_out) {
 }
 
 int device_list_size() { return g_inited ? (int)g_devices.size() : 0; }
+
+int32_t aux_stream(cudaStream_t* out) {
+    MPC_TRY(enter(nullptr));
+    if (!t_aux_streams[t_dev_index])
+        MPC_CUDA_TRY(cudaStreamCreateWithFlags(&t_aux_streams[t_dev_index], cudaStreamNonBlocking));
+    *out = t_aux_streams[t_dev_index];
+    return MPC_CUDA_OK;
+}
 
 DeviceScope::DeviceScope(int index) : saved(t_dev_index), rc(MPC_CUDA_OK) {
     if (index < 0 || index >= (int)g_devices.size()) {
@@ -290,6 +299,9 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "msm_affine")) {
         MPC_ARG_CHECK(value >= 0 && value <= 3);
         g_opt_msm_affine = value;
+    } else if (!strcmp(name, "msm_affine_split")) {
+        MPC_ARG_CHECK(value >= 0 && value <= 2);
+        g_opt_msm_affine_split = value;
     } else if (!strcmp(name, "msm_host_chunks")) {
         MPC_ARG_CHECK(value >= 0 && value <= 16);
         g_opt_msm_host_chunks = value;

@@ -20,6 +20,7 @@
 //               k_horner          warp-cooperative Σ_w 2^(cw) S_w        k_emit   affine / Jacobian result
 #pragma once
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "ec.cuh"
@@ -834,6 +835,82 @@ __global__ void __launch_bounds__(ACC_THREADS) k_generate(Affine<F> gen, uint64_
     store_pod(out + i, r);
 }
 
+// The same round as two kernels.  The product (forward) pass is memory-bound — two random x gathers and one product
+// per pair — and the addition (backward) pass multiplier-bound; fused in one kernel the first costs a third of the
+// round.  Split, the forward kernel of segment j+1 runs on a second stream underneath the backward kernel of segment
+// j (MsmJob::affine_round): its prefix products and per-lane totals travel through global memory.
+constexpr int AFF_FWD_THREADS = 64;
+
+template <class F, bool GATHER>
+__global__ void __launch_bounds__(AFF_FWD_THREADS) k_affine_fwd(const Affine<F>* __restrict__ pts,
+                                                                const uint32_t* __restrict__ idx, size_t npairs, int batch,
+                                                                size_t wb_lo, size_t wb_hi, F* __restrict__ pre,
+                                                                F* __restrict__ totals) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t wb = wb_lo + warp; wb < wb_hi; wb += nwarps) {
+        const size_t base = wb * (32 * (size_t)batch);
+        F run = F::one();
+        for (int k = 0; k < batch; k++) {
+            Affine<F> a, b;
+            F d;
+            const size_t i = base + (size_t)k * 32 + lane;
+            aff_load_pair<F, GATHER, false>(pts, idx, i, npairs, a, b, d);
+            store_pod(pre + i, run);
+            run = mul(run, d);
+        }
+        store_pod(totals + wb * 32 + lane, run);
+    }
+}
+
+template <class F, bool GATHER>
+__global__ void __launch_bounds__(AFF_THREADS, sizeof(F) > 48 ? 1 : AFF_MIN_BLOCKS) k_affine_bwd(
+    const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, size_t npairs, int batch, size_t wb_lo, size_t wb_hi,
+    const F* __restrict__ pre, const F* __restrict__ totals, Affine<F>* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t wb = wb_lo + warp; wb < wb_hi; wb += nwarps) {
+        const size_t base = wb * (32 * (size_t)batch);
+        F run = load_pod(totals + wb * 32 + lane);
+        F pfx = run, sfx = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            F up = warp_shfl_up(pfx, off), dn = warp_shfl_down(sfx, off);
+            if (lane >= (uint32_t)off) pfx = mul(pfx, up);
+            if (lane + off < 32) sfx = mul(sfx, dn);
+        }
+        F total = warp_bcast(pfx, 31);
+        F before = warp_shfl_up(pfx, 1), after = warp_shfl_down(sfx, 1);
+        F inv_run = inv_euclid(total);
+        if (lane > 0) inv_run = mul(inv_run, before);
+        if (lane < 31) inv_run = mul(inv_run, after);
+        for (int k = batch - 1; k >= 0; k--) {
+            const size_t i = base + (size_t)k * 32 + lane;
+            Affine<F> a, b, r;
+            F d;
+            int kind = aff_load_pair<F, GATHER, true>(pts, idx, i, npairs, a, b, d);
+            F dinv = mul(inv_run, load_pod(pre + i));
+            inv_run = mul(inv_run, d);
+            if (kind >= 3) {
+                F lam = kind == 3 ? mul(sub(b.y, a.y), dinv) : mul(add(dbl(sqr(a.x)), sqr(a.x)), dinv);
+                F x3 = sub(sub(sqr(lam), a.x), kind == 3 ? b.x : a.x);
+                r.y = sub(mul(lam, sub(a.x, x3)), a.y);
+                r.x = x3;
+            } else if (kind == 1) {
+                r = a;
+            } else if (kind == 2) {
+                r = b;
+            } else {
+                r.x = F::zero();
+                r.y = F::zero();
+            }
+            if (i < npairs) store_pod(out + i, r);
+        }
+    }
+}
+
 // ---- host pipeline ------------------------------------------------------------------------------------
 template <class K>
 int32_t allow_smem(K kernel, size_t bytes) {
@@ -868,8 +945,20 @@ struct MsmJob {
     uint2* pairs;
     uint4* tasks;
     XYZZ<F>*buckets, *partials, *chunk_res, *wpart, *wsum;
-    Scratch s_q1, s_q2;
+    Scratch s_q1, s_q2, s_pre, s_tot;
     Affine<F>*q1 = nullptr, *q2 = nullptr;       // affine pre-reduction: pair sums, sums of four
+    F *aff_pre = nullptr, *aff_tot = nullptr;    // split rounds: prefix products per pair, products per lane
+    cudaStream_t s2 = nullptr;                   // producer stream of the split rounds
+    std::vector<cudaEvent_t> events;
+    bool aff_split = false;
+    ~MsmJob() {
+        for (cudaEvent_t e : events) cudaEventDestroy(e);      // released once the recorded work has completed
+    }
+    int32_t new_event(cudaEvent_t* e) {
+        MPC_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        events.push_back(*e);
+        return MPC_CUDA_OK;
+    }
     size_t nbuckets = 0;
     int acc_blocks = 1, aff_blocks_g = 1, aff_blocks_d = 1;
 
@@ -893,6 +982,17 @@ struct MsmJob {
             MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aff_blocks_d, k_affine_pairs<F, false>, AFF_THREADS, 0));
             if (aff_blocks_g < 1) aff_blocks_g = 1;
             if (aff_blocks_d < 1) aff_blocks_d = 1;
+            // opt-in two-kernel pipeline: needs the prefix products in global memory. Measured SLOWER than the fused
+            // kernel (2^24 points, c = 22: 83.9 vs 78.5 ms; 2^22: 28.1 vs 25.0 ms - the prefix products' round trip
+            // through HBM costs more than the overlap wins), so the fused kernel stays the default.
+            const size_t pairs0 = (size_t)p.snwin * p.snp / 2;
+            aff_split = g_opt_msm_affine_split.load(std::memory_order_relaxed) == 1;
+            if (aff_split) {
+                const size_t span = 32 * (size_t)AFF_B;
+                MPC_TRY(s_pre.alloc(&aff_pre, (pairs0 + span - 1) / span * span + span, s));
+                MPC_TRY(s_tot.alloc(&aff_tot, pairs0 / 16 + 64, s));        // >= 32 lanes per batch of >= 16 pairs per lane
+                MPC_TRY(aux_stream(&s2));
+            }
         }
         MPC_TRY(s_pairs.alloc(&pairs, (size_t)p.nwin * cap, s));
         MPC_TRY(s_hist.alloc(&hist, (size_t)p.snwin * p.chunks * hbins, s));
@@ -966,20 +1066,8 @@ struct MsmJob {
         if (p.aff) {
             // pairwise affine additions inside every bucket's padded run, then XYZZ accumulation of what is left
             const size_t slots = (size_t)p.snwin * p.snp;
-            // pairs per lane per shared inversion: at least ~4 batches for every resident warp
-            auto batch_for = [&](size_t npairs, int blocks) {
-                size_t lanes = (size_t)dev->sm_count * blocks * AFF_THREADS;
-                size_t b = npairs / (lanes * 4);
-                return (int)(b < 16 ? 16 : b > AFF_B ? AFF_B : b);
-            };
-            k_affine_pairs<F, true><<<dev->sm_count * aff_blocks_g, AFF_THREADS, 0, s>>>(points, sorted, slots / 2, q1,
-                                                                                    batch_for(slots / 2, aff_blocks_g));
-            MPC_KERNEL_CHECK();
-            if (p.aff > 1) {
-                k_affine_pairs<F, false><<<dev->sm_count * aff_blocks_d, AFF_THREADS, 0, s>>>(q1, nullptr, slots / 4, q2,
-                                                                                         batch_for(slots / 4, aff_blocks_d));
-                MPC_KERNEL_CHECK();
-            }
+            MPC_TRY((affine_round<true>(points, sorted, slots / 2, q1, aff_blocks_g)));
+            if (p.aff > 1) MPC_TRY((affine_round<false>(q1, nullptr, slots / 4, q2, aff_blocks_d)));
             k_accumulate<F, true><<<acc_grid, ACC_THREADS, 0, s>>>(
                 p.aff > 1 ? q2 : q1, nullptr, p.snp >> p.aff, p.nb, tasks, counters, buckets, partials, merge);
         } else {
@@ -999,6 +1087,44 @@ struct MsmJob {
         profile_end("msm_reduce", s);
         done += len;
         nchunks++;
+        return MPC_CUDA_OK;
+    }
+
+    // one pre-reduction round over `npairs` pairs: the fused kernel, or forward / backward kernels pipelined over
+    // two streams in segments of whole warp batches
+    template <bool GATHER>
+    int32_t affine_round(const Affine<F>* pts, const uint32_t* idx, size_t npairs, Affine<F>* out, int blocks) {
+        // pairs per lane per shared inversion: at least ~4 batches for every resident warp
+        const size_t lanes = (size_t)dev->sm_count * blocks * AFF_THREADS;
+        size_t b = npairs / (lanes * 4);
+        const int batch = (int)(b < 16 ? 16 : b > (size_t)AFF_B ? (size_t)AFF_B : b);
+        const size_t nwb = (npairs + 32 * (size_t)batch - 1) / (32 * (size_t)batch);       // warp batches
+        const int segments = !aff_split ? 0 : nwb >= 4096 ? 8 : nwb >= 8 ? 4 : 1;
+        if (segments == 0) {
+            k_affine_pairs<F, GATHER><<<dev->sm_count * blocks, AFF_THREADS, 0, s>>>(pts, idx, npairs, out, batch);
+            MPC_KERNEL_CHECK();
+            return MPC_CUDA_OK;
+        }
+        // the producer stream may start once everything enqueued so far on s (sort, previous round's readers of
+        // aff_pre / aff_tot) is done
+        cudaEvent_t ready;
+        MPC_TRY(new_event(&ready));
+        MPC_CUDA_TRY(cudaEventRecord(ready, s));
+        MPC_CUDA_TRY(cudaStreamWaitEvent(s2, ready, 0));
+        const unsigned fwd_grid = (unsigned)std::min<size_t>((size_t)dev->sm_count * 4, (nwb * 32 + AFF_FWD_THREADS - 1) / AFF_FWD_THREADS);
+        const unsigned bwd_grid = (unsigned)std::min<size_t>((size_t)dev->sm_count * blocks, (nwb * 32 + AFF_THREADS - 1) / AFF_THREADS);
+        for (int c = 0; c < segments; c++) {
+            const size_t lo = nwb * c / segments, hi = nwb * (c + 1) / segments;
+            if (lo == hi) continue;
+            k_affine_fwd<F, GATHER><<<fwd_grid, AFF_FWD_THREADS, 0, s2>>>(pts, idx, npairs, batch, lo, hi, aff_pre, aff_tot);
+            MPC_KERNEL_CHECK();
+            cudaEvent_t done;
+            MPC_TRY(new_event(&done));
+            MPC_CUDA_TRY(cudaEventRecord(done, s2));
+            MPC_CUDA_TRY(cudaStreamWaitEvent(s, done, 0));
+            k_affine_bwd<F, GATHER><<<bwd_grid, AFF_THREADS, 0, s>>>(pts, idx, npairs, batch, lo, hi, aff_pre, aff_tot, out);
+            MPC_KERNEL_CHECK();
+        }
         return MPC_CUDA_OK;
     }
 
