@@ -7,6 +7,9 @@ import numpy as np
 import __graft_entry__ as ge
 pkg = ge.load_package(); H, S, L = pkg.host, pkg.synth, pkg._lib
 H.init(); H.set_party(0, 1)
+if os.environ.get("L2_FETCH"):                      # cudaLimitMaxL2FetchGranularity hint: 32, 64 or 128
+    H.set_option("l2_fetch_granularity", int(os.environ["L2_FETCH"]))
+MODES = ((False, True) if not os.environ.get("TABLE_ONLY") else (True,))
 STAGES = ("msm_total", "msm_sort", "msm_accumulate", "msm_reduce")
 for log_n in [int(x) for x in sys.argv[1:]] or [18, 20, 22, 24]:
     n = 1 << log_n
@@ -14,7 +17,7 @@ for log_n in [int(x) for x in sys.argv[1:]] or [18, 20, 22, 24]:
     dev = H.g1_generate(seed, n)
     sc = H.DeviceBuffer(n * 32).upload(S.fr_uniform(seed, n))
     out = H.DeviceBuffer(144)
-    for table in (False, True):
+    for table in MODES:
         h = H.register_bases_dev(dev, n)
         if table:
             h.precompute(0)

@@ -299,6 +299,11 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "msm_affine")) {
         MPC_ARG_CHECK(value >= 0 && value <= 3);
         g_opt_msm_affine = value;
+    } else if (!strcmp(name, "l2_fetch_granularity")) {
+        // hint to the driver (cudaLimitMaxL2FetchGranularity) for the calling thread's device: 32, 64 or 128 bytes
+        MPC_ARG_CHECK(value == 32 || value == 64 || value == 128);
+        MPC_TRY(enter(nullptr));
+        MPC_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
     } else if (!strcmp(name, "msm_affine_split")) {
         MPC_ARG_CHECK(value >= 0 && value <= 2);
         g_opt_msm_affine_split = value;

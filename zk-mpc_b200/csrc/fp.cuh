@@ -176,11 +176,14 @@ HD uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo;
 template <class P>
 HD void wredc_row(uint64_t* ev, uint64_t* od) {
     constexpr int H = P::N / 2;
-    uint32_t m = ptx::mul_lo(lo32(ev[0]), P::INV);
+    // both BLS12-377 moduli are 1 mod 2^32, so -p^-1 = -1: m is a negation and m * p_0 a plain 64-bit addition
+    // (the low limb cancels to zero, its carry enters limb 1) - one multiplier slot less per row
+    constexpr bool UNIT = P::mod(0) == 1u && P::INV == 0xffffffffu;
+    uint32_t m = UNIT ? 0u - lo32(ev[0]) : ptx::mul_lo(lo32(ev[0]), P::INV);
     od[0] = ptx::madw_cc(P::mod(1), m, od[0]);
 #pragma unroll
     for (int k = 1; k < H; k++) od[k] = ptx::madwc_cc(P::mod(2 * k + 1), m, od[k]);   // no carry out
-    ev[0] = ptx::madw_cc(P::mod(0), m, ev[0]);
+    ev[0] = UNIT ? ptx::add64_cc(ev[0], (uint64_t)m) : ptx::madw_cc(P::mod(0), m, ev[0]);
 #pragma unroll
     for (int k = 1; k < H; k++) ev[k] = ptx::madwc_cc(P::mod(2 * k), m, ev[k]);
     od[H - 1] = pack64(lo32(od[H - 1]), ptx::addc(hi32(od[H - 1]), 0));                  // carry -> limb N

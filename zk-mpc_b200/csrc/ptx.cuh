@@ -49,6 +49,7 @@ HD uint64_t madw_cc(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; asm volati
 HD uint64_t madwc_cc(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; asm volatile("{ .reg .u64 t; mul.wide.u32 t, %1, %2; addc.cc.u64 %0, %3, t; }" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
 HD uint64_t madwc(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; asm volatile("{ .reg .u64 t; mul.wide.u32 t, %1, %2; addc.u64 %0, %3, t; }" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
 
+HD uint64_t add64_cc(uint64_t a, uint64_t b) { uint64_t r; asm volatile("add.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 HD uint64_t addc64_cc(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 HD uint64_t addc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
@@ -75,6 +76,7 @@ HD uint64_t mulw(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
 HD uint64_t madw_cc(uint32_t a, uint32_t b, uint64_t c) { unsigned __int128 t = (unsigned __int128)((uint64_t)a * b) + c; g_cc = (uint32_t)(t >> 64); return (uint64_t)t; }
 HD uint64_t madwc_cc(uint32_t a, uint32_t b, uint64_t c) { unsigned __int128 t = (unsigned __int128)((uint64_t)a * b) + c + g_cc; g_cc = (uint32_t)(t >> 64); return (uint64_t)t; }
 HD uint64_t madwc(uint32_t a, uint32_t b, uint64_t c) { return (uint64_t)a * b + c + g_cc; }
+HD uint64_t add64_cc(uint64_t a, uint64_t b) { unsigned __int128 t = (unsigned __int128)a + b; g_cc = (uint32_t)(t >> 64); return (uint64_t)t; }
 HD uint64_t addc64_cc(uint64_t a, uint64_t b) { unsigned __int128 t = (unsigned __int128)a + b + g_cc; g_cc = (uint32_t)(t >> 64); return (uint64_t)t; }
 HD uint64_t addc64(uint64_t a, uint64_t b) { return a + b + g_cc; }
 
