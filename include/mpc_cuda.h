@@ -243,6 +243,17 @@ int32_t mpc_cuda_poly_div_linear(const uint64_t* coeffs, size_t n, const uint64_
                                  uint64_t* rem_out);
 int32_t mpc_cuda_poly_div_linear_dev(const uint64_t* coeffs, size_t n, const uint64_t* z_mont_host, uint64_t* q_out,
                                      uint64_t* rem_out, void* stream);
+/* f4: p(x) = q(x) (x^m - 1) + rem on the local share values of p's n coefficients, and p(x) (x^m - 1): Marlin's
+ * divide_by_vanishing_poly / mul_by_vanishing_poly on shared polynomials (arkworks/algebra/poly/src/polynomial/
+ * univariate/dense.rs:155-173 -> univariate/mod.rs:133-143 -> mpc-algebra/src/share/additive.rs:154-162), as
+ * AHPForR1CS::prover_first_round / prover_second_round call them (arkworks/marlin/src/ahp/prover.rs:352,364,507,543).
+ * q_out receives n - m coefficients (nothing when n <= m; NULL: remainder only), rem_out m coefficients, out n + m.
+ * Fixed-size arrays as above (the reference truncates leading zeros). */
+int32_t mpc_cuda_poly_div_vanishing(const uint64_t* coeffs, size_t n, size_t m, uint64_t* q_out, uint64_t* rem_out);
+int32_t mpc_cuda_poly_div_vanishing_dev(const uint64_t* coeffs, size_t n, size_t m, uint64_t* q_out, uint64_t* rem_out,
+                                        void* stream);
+int32_t mpc_cuda_poly_mul_vanishing(const uint64_t* coeffs, size_t n, size_t m, uint64_t* out);
+int32_t mpc_cuda_poly_mul_vanishing_dev(const uint64_t* coeffs, size_t n, size_t m, uint64_t* out, void* stream);
 
 /* ---- share MSM ------------------------------------------------------------------------------
  * Msm::msm / AffineMsm::msm (mpc-algebra/src/share/msm.rs:6-9,33-37) =

@@ -402,3 +402,130 @@ def groth16_prove(pkarr, mats, num_inputs, z, log_n, r, s, threads=8):
     for t in (t3, l_acc, h_acc):
         g_c = g1_add(g_c[0], t[0], g_c[1], t[1])
     return {"a": g_a, "b": g2_b, "c": g_c, "h": h}
+
+
+# ----------------------------------------------------------------------------- Marlin AHP rounds on plain values
+FR_MODULUS = 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001
+
+
+def fr_to_ints(a):
+    """(n,4) Montgomery limbs -> python ints"""
+    c = fr("from_mont", _a(a, 4).reshape(-1, 4))
+    return [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in c]
+
+
+def fr_from_ints(vals):
+    m = (1 << 64) - 1
+    c = np.array([[v & m, (v >> 64) & m, (v >> 128) & m, (v >> 192) & m] for v in vals], dtype=np.uint64).reshape(-1, 4)
+    return fr("to_mont", c) if len(c) else c
+
+
+def _trim(ints):
+    ints = list(ints)
+    while ints and ints[-1] == 0:
+        ints.pop()
+    return ints
+
+
+def _next_pow2(size):
+    return 1 << max(size - 1, 0).bit_length()
+
+
+def _ntt_ints(vals, n, kind):
+    v = list(vals) + [0] * (n - len(vals))
+    assert len(v) == n
+    return fr_to_ints(ntt(fr_from_ints(v), kind))
+
+
+def _div_ints(num, den):
+    q, r = poly_div(fr_from_ints(num), fr_from_ints(den))
+    return fr_to_ints(q) if len(q) else [], fr_to_ints(r) if len(r) else []
+
+
+def _vanishing(n):
+    return [FR_MODULUS - 1] + [0] * (n - 1) + [1]
+
+
+def marlin_rounds(mats, num_constraints, num_inputs, x, w, blinders, mask, alpha, etas):
+    """AHPForR1CS::prover_init / prover_first_round / prover_second_round (arkworks/marlin/src/ahp/prover.rs:212-566)
+    for a single party holding the opened values, every polynomial a truncated list of python ints.  mats = three
+    (row_ptr, col, coeff_ints) square matrices; x, w, blinders, mask, alpha, etas python ints."""
+    P = FR_MODULUS
+    nh, nx = _next_pow2(num_constraints), _next_pow2(num_inputs)
+    assert nx == num_inputs and len(x) + len(w) == num_constraints
+    z = list(x) + list(w)
+
+    def inner(mat):                                            # prover.rs:258-278
+        row_ptr, col, coeff = mat
+        return [sum(coeff[k] * z[col[k]] for k in range(row_ptr[r], row_ptr[r + 1])) % P for r in range(num_constraints)]
+
+    z_a, z_b = inner(mats[0]), inner(mats[1])
+    # first round (prover.rs:321-374)
+    x_poly = _trim(_ntt_ints(x, nx, "ifft"))
+    x_evals = _ntt_ints(x_poly, nh, "fft")
+    ratio = nh // nx
+    w_ext = list(w) + [0] * (nh - nx - len(w))
+    w_evals = [0 if k % ratio == 0 else (w_ext[k - k // ratio - 1] - x_evals[k]) % P for k in range(nh)]
+
+    def blind(evals, r):
+        p = _ntt_ints(evals, nh, "ifft") + [0]
+        p[nh] = r % P
+        p[0] = (p[0] - r) % P
+        return _trim(p)
+
+    w_poly, rem = _div_ints(blind(w_evals, blinders[0]), _vanishing(nx))
+    assert not rem, "w(x) + r v_H must vanish on the input domain"
+    z_a_poly, z_b_poly = blind(z_a, blinders[1]), blind(z_b, blinders[2])
+    mask = list(mask)
+    assert len(mask) == 3 * nh + 2 * 1 - 2
+    _, mrem = _div_ints(mask, _vanishing(nh))
+    mask[0] = (mask[0] - (mrem[0] if mrem else 0)) % P
+    mask = _trim(mask)
+    # second round (prover.rs:461-545)
+    def poly_mul(a, b):                                        # dense.rs:567-583
+        if not a or not b:
+            return []
+        n = _next_pow2(len(a) + len(b))
+        ea, eb = _ntt_ints(a, n, "fft"), _ntt_ints(b, n, "fft")
+        return _trim(_ntt_ints([u * v % P for u, v in zip(ea, eb)], n, "ifft"))
+
+    z_c = poly_mul(z_a_poly, z_b_poly)
+    summed = [c * etas[2] % P for c in z_c]
+    for i, (a, b) in enumerate(zip(z_a_poly, z_b_poly)):
+        if i < len(summed):
+            summed[i] = (summed[i] + etas[0] * a + etas[1] * b) % P
+    summed = _trim(summed)
+    gen = fr_to_ints(domain_params(nh.bit_length() - 1)["group_gen"].reshape(1, 4))[0]
+    vanish_alpha = (pow(alpha, nh, P) - 1) % P
+    r_evals, h = [], 1
+    for _ in range(nh):                                        # ahp/mod.rs:357-364
+        r_evals.append(vanish_alpha * pow((alpha - h) % P, P - 2, P) % P)
+        h = h * gen % P
+    r_alpha = _trim(_ntt_ints(r_evals, nh, "ifft"))
+    t_evals = [0] * nh                                         # calculate_t, prover.rs:406-423
+    period = nh // nx
+    for (row_ptr, col, coeff), eta in zip(mats, etas):
+        for r in range(num_constraints):
+            for k in range(row_ptr[r], row_ptr[r + 1]):
+                c = col[k]
+                if c < nx:
+                    idx = c * period
+                else:
+                    i = c - nx
+                    idx = i + i // (period - 1) + 1
+                t_evals[idx] = (t_evals[idx] + eta * coeff[k] * r_evals[r]) % P
+    t_poly = _trim(_ntt_ints(t_evals, nh, "ifft"))
+    z_poly = [0] * nx + list(w_poly)                           # mul_by_vanishing_poly, dense.rs:155-162
+    for i, c in enumerate(w_poly):
+        z_poly[i] = (z_poly[i] - c) % P
+    for i, c in enumerate(x_poly):
+        z_poly[i] = (z_poly[i] + c) % P
+    z_poly = _trim(z_poly)
+    mul_n = _next_pow2(max(len(mask), len(r_alpha) + len(summed), len(t_poly) + len(z_poly)))
+    ev = lambda p: _ntt_ints(p, mul_n, "fft")
+    a, b, c, d = ev(r_alpha), ev(summed), ev(z_poly), ev(t_poly)
+    rhs = _trim(_ntt_ints([(a[i] * b[i] - c[i] * d[i]) % P for i in range(mul_n)], mul_n, "ifft"))
+    q_1 = [((mask[i] if i < len(mask) else 0) + (rhs[i] if i < len(rhs) else 0)) % P for i in range(max(len(mask), len(rhs)))]
+    h_1, x_g_1 = _div_ints(_trim(q_1), _vanishing(nh))
+    return dict(z_a=z_a, z_b=z_b, w=w_poly, z_a_poly=z_a_poly, z_b_poly=z_b_poly, mask=mask, z_c=z_c, t=t_poly,
+                g_1=x_g_1[1:], h_1=h_1, x_g_1_0=x_g_1[0] if x_g_1 else 0)

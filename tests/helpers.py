@@ -81,3 +81,18 @@ class ThreadNet:
 
 def oracle_groth16(orc, pkarr, mats, num_inputs, z, log_n, r, s):
     return orc.groth16_prove(pkarr, mats, num_inputs, z, log_n, r, s)
+
+
+# ----------------------------------------------------------------------------- synthetic Marlin instances
+def synth_marlin_instance(pkg, orc, seed, num_constraints, num_inputs, max_terms=3):
+    """a satisfied square R1CS: random sparse A, B over a random assignment z = [x | w] with z_0 = 1, and C with one
+    entry per row at column 0 carrying (Az)_r (Bz)_r.  Returns (mats as limb arrays, mats as int lists, x, w limbs)."""
+    S = pkg.synth
+    a, b, _ = S.r1cs_matrices(seed, num_constraints, num_constraints, max_terms)
+    z = S.fr_uniform(seed + 1, num_constraints)
+    z[0] = S.FR_R_LIMBS
+    za, zb = orc.spmv(*a, z), orc.spmv(*b, z)
+    c = (np.arange(num_constraints + 1, dtype=np.uint64), np.zeros(num_constraints, dtype=np.uint32), orc.vec_op("mul", za, zb))
+    mats = [a, b, c]
+    ints = [([int(v) for v in m[0]], [int(v) for v in m[1]], orc.fr_to_ints(m[2])) for m in mats]
+    return mats, ints, z[:num_inputs], z[num_inputs:]

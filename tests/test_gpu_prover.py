@@ -448,3 +448,95 @@ def test_groth16_prove_sequence_spdz(H, orc, pkg):
     bad[1][ni + 7, 0] ^= np.uint64(1)                       # one party's MAC share of one witness value is off
     res = run(bad)
     assert all(isinstance(r, H.MpcCudaError) and "MAC check" in str(r) for r in res)
+
+
+def test_poly_div_and_mul_by_vanishing(H, orc, pkg):
+    """divide_by_vanishing_poly / mul_by_vanishing_poly on local share values (dense.rs:155-173 through
+    univariate_div_qr): against the oracle's literal long division, for short divisors (long columns, chunked scan),
+    divisors longer than the dividend, ragged lengths, and (q, r) recombined"""
+    S = pkg.synth
+    one = S.FR_R_LIMBS
+    for n, m in ((1, 1), (5, 8), (8, 8), (9, 8), (1000, 1), (1000, 2), (4097, 16), (3 * 1024, 1024), (70001, 4), (5000, 4096),
+                 (300000, 2)):
+        p = S.fr_uniform(0x4A00 + n + m, n)
+        den = np.zeros((m + 1, 4), dtype=np.uint64)
+        den[m] = one
+        den[0] = orc.fr("neg", one[None])[0]
+        q, r = H.poly_div_vanishing(p, m)
+        eq, er = orc.poly_div(p, den)
+        assert q.shape == (max(n - m, 0), 4) and r.shape == (m, 4)
+        assert np.array_equal(q[:len(eq)], eq) and not q[len(eq):].any(), (n, m)
+        assert np.array_equal(r[:len(er)], er) and not r[len(er):].any(), (n, m)
+        prod = H.poly_mul_vanishing(p, m)
+        shifted = np.zeros((n + m, 4), dtype=np.uint64)
+        shifted[m:] = p
+        low = np.zeros((n + m, 4), dtype=np.uint64)
+        low[:n] = p
+        assert np.array_equal(prod, orc.vec_op("sub", shifted, low)), (n, m)
+        if n > m:                                               # q v + r = p
+            back = H.poly_mul_vanishing(q, m)
+            back[:m] = orc.fr("add", back[:m], r)
+            assert np.array_equal(back, p), (n, m)
+    with pytest.raises(pkg._lib.MpcCudaError):
+        pkg._lib.call("mpc_cuda_poly_div_vanishing", None, 4, 2, None, None)
+
+
+@pytest.mark.parametrize("nc,ni", [(50, 2), (256, 4), (1000, 8), (64, 1)])
+def test_marlin_rounds_three_parties(H, orc, pkg, nc, ni):
+    """AHPForR1CS::prover_init / first / second round (arkworks/marlin/src/ahp/prover.rs:212-566) for 3 parties as 3
+    threads on additive shares of the witness, the blinders and the mask polynomial, z_A * z_B through a Beaver batch
+    product with wire-level opens.  Every oracle the prover would commit to, summed over the parties, must equal the
+    plain prover's (oracle.marlin_rounds) coefficient for coefficient; the extra high coefficients the shared prover
+    carries (it cannot truncate shared polynomials) must open to zero; t is public and identical at every party."""
+    M, S = pkg.marlin, pkg.synth
+    parties = 3
+    mats, ints, x, w = helpers.synth_marlin_instance(pkg, orc, 0x5A00 + nc, nc, ni)
+    nh = 1 << max(nc - 1, 0).bit_length()
+    rnd = S.fr_uniform(0x5B00 + nc, 3 * nh + 16)
+    blinders, alpha, etas, mask = rnd[:3], rnd[3], rnd[4:7], rnd[8:8 + 3 * nh]
+    I = orc.fr_to_ints
+    exp = orc.marlin_rounds(ints, nc, ni, I(x), I(w), I(blinders), I(mask), I(alpha[None])[0], I(etas))
+    w_sh, bl_sh, mask_sh = (_shares_of(orc, pkg, 0x5C00 + 16 * k, v) for k, v in enumerate((w, blinders, mask)))
+    tx_o, ty_o = S.fr_uniform(0x5D00, 4 * nh), S.fr_uniform(0x5D01, 4 * nh)
+    tz_o = orc.vec_op("mul", tx_o, ty_o)
+    tx, ty, tz = (_shares_of(orc, pkg, 0x5E00 + 16 * k, v) for k, v in enumerate((tx_o, ty_o, tz_o)))
+    nets = helpers.ThreadNet.make(parties)
+    ready = threading.Barrier(parties)
+    state = {}
+
+    def party(p):
+        H.set_party(p, parties)
+        H.set_device(0)
+        if p == 0:
+            state["index"] = M.Index(mats, nc, ni)
+        ready.wait()
+        index, leader = state["index"], p == 0
+        z_a, z_b = M.prover_init(index, x, w_sh[p], leader)
+        first = M.prover_first_round(index, x, w_sh[p], z_a, z_b, bl_sh[p], mask_sh[p], leader)
+        second = M.prover_second_round(index, first, x, alpha, etas, nets[p], (tx[p], ty[p], tz[p]), leader)
+        return dict(z_a_evals=z_a, z_b_evals=z_b, **first, **second)
+
+    outs = _run_parties(party, parties)
+    H.set_party(0, 3)
+    state["index"].release()
+
+    def opened(key):
+        return I(orc.open_sum(np.stack([o[key] for o in outs])))
+
+    def same_poly(got, want, what):
+        assert got[:len(want)] == want, what
+        assert not any(got[len(want):]), what + ": high coefficients must open to zero"
+
+    same_poly(opened("z_a_evals"), exp["z_a"], "z_A evaluations")
+    same_poly(opened("z_b_evals"), exp["z_b"], "z_B evaluations")
+    same_poly(opened("w"), exp["w"], "w")
+    same_poly(opened("z_a"), exp["z_a_poly"], "z_A")
+    same_poly(opened("z_b"), exp["z_b_poly"], "z_B")
+    same_poly(opened("mask"), exp["mask"], "mask")
+    same_poly(opened("z_c"), exp["z_c"], "z_A z_B")
+    same_poly(opened("g_1"), exp["g_1"], "g_1")
+    same_poly(opened("h_1"), exp["h_1"], "h_1")
+    for o in outs:
+        assert I(o["t"]) == exp["t"]
+        assert o["mul_domain"] == (8 * nh).bit_length() - 1     # untruncated shared lengths: 8|H| (plain prover: 4|H|)
+    assert len(outs[0]["w"]) == nh + 1 - ni and len(outs[0]["z_c"]) == 4 * nh and len(outs[0]["h_1"]) == 7 * nh

@@ -15,3 +15,4 @@ from . import sharding  # noqa: F401
 from . import wire  # noqa: F401
 from . import groth16  # noqa: F401
 from . import kzg  # noqa: F401
+from . import marlin  # noqa: F401

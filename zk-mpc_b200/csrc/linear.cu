@@ -304,6 +304,100 @@ int32_t poly_div_linear_dev(const Fr* p, size_t n, const uint64_t* z_host, Fr* q
     return MPC_CUDA_OK;
 }
 
+// ---------------------------------------------------------------------- f4: division by / product with x^m - 1
+// p = q (x^m - 1) + r on the local values of p's n coefficients (Marlin's divide_by_vanishing_poly on shares:
+// poly/src/polynomial/univariate/dense.rs:166-173 -> mod.rs:133-143 -> share/additive.rs:154-162).  With the
+// coefficients laid out as K = ceil(n / m) rows of m columns, q[k][c] is the sum of column c strictly below row k
+// and r[c] = p[0][c] + q[0][c]: a suffix scan down every column.  Rows are cut into `chunks` runs of R rows so a
+// short divisor (the public-input domain) still fills the device: run sums, a scan over the runs, then the emit.
+constexpr size_t VAN_TARGET_THREADS = (size_t)1 << 18;
+constexpr size_t VAN_MAX_CHUNKS = 4096;
+
+__global__ void __launch_bounds__(LIN_THREADS) k_van_sums(const Fr* __restrict__ p, size_t n, size_t m, size_t K, size_t R,
+                                                         size_t chunks, Fr* __restrict__ sums) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks * m) return;
+    size_t chunk = t / m, col = t % m;
+    size_t lo = chunk * R, hi = lo + R < K ? lo + R : K;
+    Fr acc = Fr::zero();
+    for (size_t row = lo; row < hi; row++) {
+        size_t idx = row * m + col;
+        if (idx < n) acc = add(acc, load_fe_ro(p + idx));
+    }
+    store_fe(sums + t, acc);
+}
+
+// one thread per column: sums[chunk][col] <- sum of the runs below it
+__global__ void __launch_bounds__(LIN_THREADS) k_van_scan(Fr* __restrict__ sums, size_t m, size_t chunks) {
+    size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= m) return;
+    Fr carry = Fr::zero();
+    for (size_t chunk = chunks; chunk-- > 0;) {
+        Fr v = load_fe(sums + chunk * m + col);
+        store_fe(sums + chunk * m + col, carry);
+        carry = add(carry, v);
+    }
+}
+
+__global__ void __launch_bounds__(LIN_THREADS) k_van_emit(const Fr* __restrict__ p, size_t n, size_t m, size_t K, size_t R,
+                                                         size_t chunks, const Fr* __restrict__ sums, Fr* __restrict__ q,
+                                                         Fr* __restrict__ rem) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks * m) return;
+    size_t chunk = t / m, col = t % m;
+    size_t lo = chunk * R, hi = lo + R < K ? lo + R : K;
+    Fr carry = sums ? load_fe(sums + t) : Fr::zero();
+    for (size_t row = hi; row-- > lo;) {
+        size_t idx = row * m + col;
+        Fr v = idx < n ? load_fe_ro(p + idx) : Fr::zero();
+        if (q && idx + m < n) store_fe(q + idx, carry);
+        if (row == 0) store_fe(rem + col, add(v, carry));
+        carry = add(carry, v);
+    }
+}
+
+// out (n + m elements) = p * (x^m - 1): the coefficients shifted up by m minus themselves (dense.rs:155-162)
+__global__ void __launch_bounds__(LIN_THREADS) k_van_mul(const Fr* __restrict__ p, size_t n, size_t m, Fr* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + m) return;
+    Fr hi = i >= m ? load_fe_ro(p + i - m) : Fr::zero();
+    Fr lo = i < n ? load_fe_ro(p + i) : Fr::zero();
+    store_fe(out + i, sub(hi, lo));
+}
+
+// q (n - m elements when n > m, may be null) and rem (m elements) on the device; neither may alias p
+int32_t poly_div_vanishing_dev(const Fr* p, size_t n, size_t m, Fr* q, Fr* rem, cudaStream_t s) {
+    MPC_ARG_CHECK(n >= 1 && n <= ((size_t)1 << 30) && m >= 1 && m <= ((size_t)1 << 30) && p && rem && (const Fr*)q != p &&
+                  (const Fr*)rem != p);
+    const size_t K = (n + m - 1) / m;
+    size_t chunks = VAN_TARGET_THREADS / m;
+    if (chunks > VAN_MAX_CHUNKS) chunks = VAN_MAX_CHUNKS;
+    if (chunks > K) chunks = K;
+    if (chunks < 1) chunks = 1;
+    const size_t R = (K + chunks - 1) / chunks;
+    chunks = (K + R - 1) / R;
+    const unsigned grid = (unsigned)((chunks * m + LIN_THREADS - 1) / LIN_THREADS);
+    Scratch ss;
+    Fr* sums = nullptr;
+    if (chunks > 1) {
+        MPC_TRY(ss.alloc(&sums, chunks * m, s));
+        k_van_sums<<<grid, LIN_THREADS, 0, s>>>(p, n, m, K, R, chunks, sums);
+        MPC_KERNEL_CHECK();
+        k_van_scan<<<(unsigned)((m + LIN_THREADS - 1) / LIN_THREADS), LIN_THREADS, 0, s>>>(sums, m, chunks);
+        MPC_KERNEL_CHECK();
+    }
+    k_van_emit<<<grid, LIN_THREADS, 0, s>>>(p, n, m, K, R, chunks, sums, n > m ? q : nullptr, rem);
+    MPC_KERNEL_CHECK();
+    return MPC_CUDA_OK;
+}
+
+int32_t poly_mul_vanishing_dev(const Fr* p, size_t n, size_t m, Fr* out, cudaStream_t s) {
+    MPC_ARG_CHECK(n >= 1 && n <= ((size_t)1 << 30) && m >= 1 && m <= ((size_t)1 << 30) && p && out && (const Fr*)out != p);
+    k_van_mul<<<(unsigned)((n + m + LIN_THREADS - 1) / LIN_THREADS), LIN_THREADS, 0, s>>>(p, n, m, out);
+    MPC_KERNEL_CHECK();
+    return MPC_CUDA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -504,6 +598,51 @@ int32_t mpc_cuda_poly_div_linear(const uint64_t* coeffs, size_t n, const uint64_
     MPC_TRY(poly_div_linear_dev(dp, n, z_mont, dq, dr, s));
     if (dq) MPC_CUDA_TRY(cudaMemcpyAsync(q_out, dq, (n - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, s));
     MPC_CUDA_TRY(cudaMemcpyAsync(rem_out, dr, sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    MPC_CUDA_TRY(cudaStreamSynchronize(s));
+    return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_poly_div_vanishing_dev(const uint64_t* coeffs, size_t n, size_t m, uint64_t* q_out, uint64_t* rem_out,
+                                        void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    return poly_div_vanishing_dev((const Fr*)coeffs, n, m, (Fr*)q_out, (Fr*)rem_out, pick_stream(stream, s));
+}
+
+int32_t mpc_cuda_poly_div_vanishing(const uint64_t* coeffs, size_t n, size_t m, uint64_t* q_out, uint64_t* rem_out) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_ARG_CHECK(coeffs && rem_out && n >= 1 && m >= 1);
+    Scratch sp, sq, sr;
+    Fr *dp, *dq = nullptr, *dr;
+    MPC_TRY(sp.alloc(&dp, n, s));
+    MPC_TRY(sr.alloc(&dr, m, s));
+    if (q_out && n > m) MPC_TRY(sq.alloc(&dq, n - m, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(dp, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    MPC_TRY(poly_div_vanishing_dev(dp, n, m, dq, dr, s));
+    if (dq) MPC_CUDA_TRY(cudaMemcpyAsync(q_out, dq, (n - m) * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(rem_out, dr, m * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    MPC_CUDA_TRY(cudaStreamSynchronize(s));
+    return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_poly_mul_vanishing_dev(const uint64_t* coeffs, size_t n, size_t m, uint64_t* out, void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    return poly_mul_vanishing_dev((const Fr*)coeffs, n, m, (Fr*)out, pick_stream(stream, s));
+}
+
+int32_t mpc_cuda_poly_mul_vanishing(const uint64_t* coeffs, size_t n, size_t m, uint64_t* out) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_ARG_CHECK(coeffs && out && n >= 1 && m >= 1);
+    Scratch sp, so;
+    Fr *dp, *dout;
+    MPC_TRY(sp.alloc(&dp, n, s));
+    MPC_TRY(so.alloc(&dout, n + m, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(dp, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    MPC_TRY(poly_mul_vanishing_dev(dp, n, m, dout, s));
+    MPC_CUDA_TRY(cudaMemcpyAsync(out, dout, (n + m) * sizeof(Fr), cudaMemcpyDeviceToHost, s));
     MPC_CUDA_TRY(cudaStreamSynchronize(s));
     return MPC_CUDA_OK;
 }

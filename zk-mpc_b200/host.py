@@ -563,3 +563,26 @@ def poly_evaluate(coeffs, z):
     rem = np.empty(4, dtype=np.uint64)
     _lib.call("mpc_cuda_poly_div_linear", _p(coeffs), C.c_size_t(coeffs.size // 4), _p(z), None, _p(rem))
     return rem
+
+
+def poly_div_vanishing(coeffs, m):
+    """(quotient, remainder) of p(x) / (x^m - 1) on local share values: quotient (max(n-m,0),4), remainder (m,4)"""
+    coeffs = _a(coeffs, 4)
+    n, m = coeffs.size // 4, int(m)
+    if n < 1 or m < 1:
+        raise ValueError("empty polynomial or domain")
+    q = np.empty((max(n - m, 0), 4), dtype=np.uint64)
+    rem = np.empty((m, 4), dtype=np.uint64)
+    _lib.call("mpc_cuda_poly_div_vanishing", _p(coeffs), C.c_size_t(n), C.c_size_t(m), _p(q) if n > m else None, _p(rem))
+    return q, rem
+
+
+def poly_mul_vanishing(coeffs, m):
+    """p(x) (x^m - 1) on local share values: (n + m, 4)"""
+    coeffs = _a(coeffs, 4)
+    n, m = coeffs.size // 4, int(m)
+    if n < 1 or m < 1:
+        raise ValueError("empty polynomial or domain")
+    out = np.empty((n + m, 4), dtype=np.uint64)
+    _lib.call("mpc_cuda_poly_mul_vanishing", _p(coeffs), C.c_size_t(n), C.c_size_t(m), _p(out))
+    return out
