@@ -160,3 +160,23 @@ pub fn poly_div_linear(coeffs: &[Fr], z: &Fr) -> (Vec<Fr>, Fr) {
     check(unsafe { ffi::mpc_cuda_poly_div_linear(lc.as_ptr(), n, lz.as_ptr(), if n > 1 { q.as_mut_ptr() } else { std::ptr::null_mut() }, rem.as_mut_ptr()) });
     (frs_from(&q), fr_from(&rem))
 }
+
+/// `(p / (x^m - 1), p mod (x^m - 1))` on local share values: `divide_by_vanishing_poly` on a shared polynomial
+/// (poly/src/polynomial/univariate/dense.rs:166-173 -> share/additive.rs:154-162; marlin/src/ahp/prover.rs:352,364,543).
+pub fn poly_div_vanishing(coeffs: &[Fr], m: usize) -> (Vec<Fr>, Vec<Fr>) {
+    assert!(!coeffs.is_empty() && m >= 1);
+    let n = coeffs.len();
+    let lc = fr_limbs(coeffs);
+    let (mut q, mut rem) = (vec![0u64; 4 * n.saturating_sub(m)], vec![0u64; 4 * m]);
+    check(unsafe { ffi::mpc_cuda_poly_div_vanishing(lc.as_ptr(), n, m, if n > m { q.as_mut_ptr() } else { std::ptr::null_mut() }, rem.as_mut_ptr()) });
+    (frs_from(&q), frs_from(&rem))
+}
+
+/// `p (x^m - 1)` on local share values (`mul_by_vanishing_poly`, dense.rs:155-162; prover.rs:507).
+pub fn poly_mul_vanishing(coeffs: &[Fr], m: usize) -> Vec<Fr> {
+    assert!(!coeffs.is_empty() && m >= 1);
+    let lc = fr_limbs(coeffs);
+    let mut out = vec![0u64; 4 * (coeffs.len() + m)];
+    check(unsafe { ffi::mpc_cuda_poly_mul_vanishing(lc.as_ptr(), coeffs.len(), m, out.as_mut_ptr()) });
+    frs_from(&out)
+}

@@ -35,6 +35,7 @@ extern "C" {
 #define MPC_CUDA_ERR_ARG 2        /* invalid argument */
 #define MPC_CUDA_ERR_NO_DEVICE 3  /* no CUDA device / init not possible */
 #define MPC_CUDA_ERR_HANDLE 4     /* unknown handle */
+#define MPC_CUDA_ERR_MAC 5        /* an SPDZ MAC check on an opened value failed (spdz.rs:177-196 panics) */
 
 /* ---- context ------------------------------------------------------------------------------- */
 /* Select the devices the library may use (NULL/0 = all visible).  Thread-safe.  Idempotent for the same
@@ -76,6 +77,10 @@ const char* mpc_cuda_version(void);
 /* device memory helpers for resident pipelines (the fused witness-map path, benchmarks) */
 int32_t mpc_cuda_malloc(void** dptr, size_t bytes);
 int32_t mpc_cuda_free(void* dptr);
+/* page-locked host memory for buffers that cross PCIe on every proof (wire payloads, triple shares): copies from
+ * pageable memory are staged by the driver at a fraction of the link rate */
+int32_t mpc_cuda_host_alloc(void** hptr, size_t bytes);
+int32_t mpc_cuda_host_free(void* hptr);
 int32_t mpc_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream);
 int32_t mpc_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream);
 int32_t mpc_cuda_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
@@ -189,7 +194,20 @@ int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n
  * a[num_constraints .. num_constraints + num_inputs) = z[0 .. num_inputs) (:272-276) and zero padding to the
  * domain; assignment = instance | witness values, `planes` x cols.
  * _finish_dev: like finish, but h stays on the device (*h_dev, planes x n, valid until _release) so that it feeds
- * the h_query MSM (src/groth16.rs:106) through mpc_cuda_msm_g1_handle_scalars_dev without crossing PCIe. */
+ * the h_query MSM (src/groth16.rs:106) through mpc_cuda_msm_g1_handle_scalars_dev without crossing PCIe.
+ *
+ * The two opens at the wire level, so that nothing but wire bytes crosses PCIe between begin and finish: pass
+ * masked_a = masked_b = NULL to begin, then for which = 0 (masked_a) and 1 (masked_b)
+ *   _masked_payload   writes the party's MpcSerNet::broadcast payload of the masked vector (8 + 32 * 2^log_n bytes,
+ *                     mpc-algebra/src/channel.rs:12-28; SPDZ: the sh plane, spdz.rs:78-84) into host memory;
+ *   _open_payloads    takes every party's received payload (n_parties host pointers, party order irrelevant), sums
+ *                     them on the device (share/additive.rs:125-131) and keeps the opened vector in the state; finish
+ *                     then takes sx = NULL / oy = NULL for an open that arrived this way;
+ *   _mac_payload      SPDZ only, after _open_payloads: the local half dx = mac_share * val - mac of batch_open's MAC
+ *                     check (spdz.rs:177-196) as a payload; _mac_verify sums the parties' dx payloads and returns
+ *                     MPC_CUDA_ERR_MAC unless every element is zero.
+ * _assignment_dev: the assignment _begin_r1cs uploaded (planes x cols, valid until _release), so that the scalar
+ * vectors of the a_query / b_query / l_query MSMs (src/groth16.rs:137-160) are device-to-device copies of it. */
 int32_t mpc_cuda_witness_map_begin(const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,
                                    const uint64_t* tx, const uint64_t* ty, uint64_t* masked_a, uint64_t* masked_b,
                                    uint64_t* state);
@@ -203,6 +221,12 @@ int32_t mpc_cuda_witness_map_finish(uint64_t state, const uint64_t* tz, const ui
                                     uint32_t is_leader, uint64_t* h_out);
 int32_t mpc_cuda_witness_map_finish_dev(uint64_t state, const uint64_t* tz, const uint64_t* sx, const uint64_t* oy,
                                         uint32_t is_leader, uint64_t** h_dev);
+int32_t mpc_cuda_witness_map_masked_payload(uint64_t state, uint32_t which, uint8_t* out);
+int32_t mpc_cuda_witness_map_open_payloads(uint64_t state, uint32_t which, const uint8_t* const* payloads,
+                                           uint32_t n_parties);
+int32_t mpc_cuda_witness_map_mac_payload(uint64_t state, uint32_t which, uint32_t is_leader, uint8_t* out);
+int32_t mpc_cuda_witness_map_mac_verify(uint64_t state, const uint8_t* const* payloads, uint32_t n_parties);
+int32_t mpc_cuda_witness_map_assignment_dev(uint64_t state, uint64_t** z_dev, size_t* cols);
 int32_t mpc_cuda_witness_map_release(uint64_t state);
 
 /* ---- linear steps either side of the path -----------------------------------

@@ -1,6 +1,7 @@
 """GPU parity for the rows either side of the NTT / MSM / Beaver kernels, the SPDZ
 witness map, the wire-level packing rules (a5, a12) and the end-to-end Groth16 prove sequence (a16 / x1), all
 against the same composition on the oracle.  Bit-exact."""
+import ctypes as C
 import threading
 
 import numpy as np
@@ -540,3 +541,98 @@ def test_marlin_rounds_three_parties(H, orc, pkg, nc, ni):
         assert I(o["t"]) == exp["t"]
         assert o["mul_domain"] == (8 * nh).bit_length() - 1     # untruncated shared lengths: 8|H| (plain prover: 4|H|)
     assert len(outs[0]["w"]) == nh + 1 - ni and len(outs[0]["z_c"]) == 4 * nh and len(outs[0]["h_1"]) == 7 * nh
+
+
+# ----------------------------------------------------------------------------- the opens at the wire level
+@pytest.mark.parametrize("spdz", [False, True])
+def test_witness_map_resident_opens_match_host_route(H, orc, pkg, spdz):
+    """masked=False route (_masked_payload / _open_payloads / _mac_payload / _mac_verify / finish with sx = oy = NULL /
+    _assignment_dev) against the host-array route of the same calls: same payload bytes, same h, page-locked and
+    pageable payload buffers alike; then the error cases"""
+    S, G = pkg.synth, pkg.groth16
+    nc, ni, nv, parties = 300, 3, 320, 3
+    log_n = 9
+    n = 1 << log_n
+    mats = helpers.synth_r1cs(pkg, 0x6A0, nc, nv)
+    r1cs = G.R1CS(*mats, num_inputs=ni, num_vars=nv)
+    z_open = S.fr_uniform(0x6B0, nv)
+    sub = lambda a, b: orc.vec_op("sub", a, b)
+    sh = S.additive_shares(0x6C0, z_open, parties, ni, sub)
+    mac = S.additive_shares(0x6D0, z_open, parties, ni, sub)
+    assign = [np.stack([sh[p], mac[p]]) if spdz else sh[p] for p in range(parties)]
+    trip = []
+    for p in range(parties):
+        v = np.tile(S.FR_R_LIMBS, (n, 1)) if p == 0 else np.zeros((n, 4), dtype=np.uint64)
+        trip.append(np.stack([v, v]) if spdz else v)
+    # host-array route
+    begun = [H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, assign[p], ni, log_n, trip[p], trip[p], spdz=spdz)
+             for p in range(parties)]
+    first = lambda v: v[0] if spdz else v
+    sx = H.open_sum(np.stack([first(bg[0]) for bg in begun]))
+    oy = H.open_sum(np.stack([first(bg[1]) for bg in begun]))
+    h_host = [H.witness_map_finish(begun[p][2], trip[p], sx, oy, p == 0) for p in range(parties)]
+    # resident route
+    pinned = H.PinnedBuffer(2 * (8 + 32 * n))
+    states = [H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, assign[p], ni, log_n, trip[p], trip[p], spdz=spdz,
+                                       masked=False) for p in range(parties)]
+    assert all(st[0] is None and st[1] is None for st in states)
+    states = [st[2] for st in states]
+    for which in (0, 1):
+        pays = [H.witness_map_masked_payload(states[p], which,
+                                             out=pinned.array(np.uint8, 8 + 32 * n, which * (8 + 32 * n)) if p == 0 else None).copy()
+                for p in range(parties)]
+        for p in range(parties):
+            assert np.array_equal(pays[p], H.fr_serialize(first(begun[p][which]))), (which, p)
+        for p in range(parties):
+            H.witness_map_open_payloads(states[p], which, pays[::-1] if p == 1 else pays)     # party order is irrelevant
+        if spdz:
+            dxs = [H.witness_map_mac_payload(states[p], which, p == 0) for p in range(parties)]
+            val = sx if which == 0 else oy
+            for p in range(parties):
+                assert np.array_equal(dxs[p], H.fr_serialize(H.spdz_mac_check(val, begun[p][which][1], p == 0)))
+                H.witness_map_mac_verify(states[p], dxs)
+            bad = [d.copy() for d in dxs]
+            bad[1][8] ^= 1
+            with pytest.raises(H.MpcCudaError, match="MAC check"):
+                H.witness_map_mac_verify(states[0], bad)
+    for p in range(parties):
+        ptr, cols = H.witness_map_assignment_dev(states[p])
+        assert cols == nv
+        back = np.empty((nv, 4), dtype=np.uint64)
+        pkg._lib.call("mpc_cuda_memcpy_d2h", back.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), C.c_size_t(nv * 32), None)
+        pkg._lib.call("mpc_cuda_stream_sync", None)
+        assert np.array_equal(back, sh[p])
+        h_ptr = H.witness_map_finish_dev(states[p], trip[p], None, None, p == 0)
+        planes = 2 if spdz else 1
+        h = np.empty((planes * n, 4), dtype=np.uint64)
+        pkg._lib.call("mpc_cuda_memcpy_d2h", h.ctypes.data_as(C.c_void_p), C.c_void_p(h_ptr), C.c_size_t(h.nbytes), None)
+        pkg._lib.call("mpc_cuda_stream_sync", None)
+        assert np.array_equal(h.reshape(h_host[p].shape), h_host[p]), p
+        states[p].release()
+    # error cases: finish without the opens, MAC payload on an additive state / before the open, malformed payloads
+    st = H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, assign[0], ni, log_n, trip[0], trip[0], spdz=spdz, masked=False)[2]
+    with pytest.raises(H.MpcCudaError):
+        H.witness_map_finish_dev(st, trip[0], None, None, True)
+    with pytest.raises(H.MpcCudaError):
+        H.witness_map_mac_payload(st, 0, True)
+    pay = H.witness_map_masked_payload(st, 0)
+    wrong_len = pay.copy()
+    wrong_len[0] ^= 1
+    with pytest.raises(H.MpcCudaError, match="length prefix"):
+        H.witness_map_open_payloads(st, 0, [pay, wrong_len])
+    not_reduced = pay.copy()
+    not_reduced[8:40] = 0xFF
+    with pytest.raises(H.MpcCudaError, match="modulus"):
+        H.witness_map_open_payloads(st, 0, [not_reduced])
+    with pytest.raises(H.MpcCudaError):
+        pkg._lib.call("mpc_cuda_witness_map_masked_payload", C.c_uint64(st.state), C.c_uint32(2), pay.ctypes.data_as(C.c_void_p))
+    H.witness_map_open_payloads(st, 0, [pay])
+    H.witness_map_open_payloads(st, 1, [H.witness_map_masked_payload(st, 1)])
+    H.witness_map_finish_dev(st, trip[0], None, None, True)
+    with pytest.raises(H.MpcCudaError):                         # already finished
+        H.witness_map_open_payloads(st, 0, [pay])
+    st.release()
+    with pytest.raises(H.MpcCudaError):
+        H.witness_map_masked_payload(st, 0)
+    pinned.free()
+    r1cs.release()

@@ -1,13 +1,15 @@
 #!/usr/bin/env python3
-"""Where one party's prove call spends its wall time at the MySecretInputCircuit shape (single party, no threads)."""
+"""Where one party's prove call spends its wall time (single party, no threads): MySecretInputCircuit shape by default,
+`tools/prove_profile.py 20` for the synthetic 2^20 instance of bench.py."""
 import json, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
 import __graft_entry__ as ge
 pkg = ge.load_package(); H, S, G = pkg.host, pkg.synth, pkg.groth16
 H.init(); H.set_party(0, 1)
-nc, ni, nv = 6574, 5, 6600
-log_n = 13; n = 1 << log_n
+log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 13
+n = 1 << log_n
+nc, ni, nv = (6574, 5, 6600) if log_n == 13 else (n - 8, 5, n)
 mats = S.r1cs_matrices(0xB10 + log_n, nc, nv)
 gen1 = lambda seed, c: (lambda b: (b.download().reshape(c, 12), b.free())[0])(H.g1_generate(seed, c))
 gen2 = lambda seed, c: (lambda b: (b.download().reshape(c, 24), b.free())[0])(H.g2_generate(seed, c))
@@ -29,7 +31,7 @@ def wrap(mod, name):
     def g(*a, **k):
         t0 = time.perf_counter(); r = f(*a, **k); times[name] = times.get(name, 0) + time.perf_counter() - t0; return r
     setattr(mod, name, g)
-for nm in ("witness_map_begin_r1cs", "fr_serialize", "open_sum_deserialize", "witness_map_finish_dev", "msm_handle_dev", "sum_partials"):
+for nm in ("witness_map_begin_r1cs", "witness_map_masked_payload", "witness_map_open_payloads", "witness_map_finish_dev", "msm_handle_dev", "sum_partials"):
     wrap(H, nm)
 for it in range(5):
     times.clear()

@@ -345,6 +345,19 @@ int32_t mpc_cuda_free(void* dptr) {
     return MPC_CUDA_OK;
 }
 
+int32_t mpc_cuda_host_alloc(void** hptr, size_t bytes) {
+    MPC_TRY(enter(nullptr));
+    MPC_ARG_CHECK(hptr != nullptr && bytes > 0);
+    MPC_CUDA_TRY(cudaHostAlloc(hptr, bytes, cudaHostAllocPortable));
+    return MPC_CUDA_OK;
+}
+
+int32_t mpc_cuda_host_free(void* hptr) {
+    MPC_TRY(enter(nullptr));
+    MPC_CUDA_TRY(cudaFreeHost(hptr));
+    return MPC_CUDA_OK;
+}
+
 int32_t mpc_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream) {
     cudaStream_t s;
     MPC_TRY(enter(&s));

@@ -118,11 +118,36 @@ class ProverSession:
             p = C.c_void_p(0)
             _lib.call("mpc_cuda_stream_create", C.byref(p))
             self.streams.append(p)
+        # page-locked staging: the four wire payloads of a proof (masked a, masked b, and the SPDZ dx of each), the
+        # six tail scalars, and the dummy triple when the caller brings none
+        plen = 8 + 32 * r1cs.n
+        self.pinned = [H.PinnedBuffer(4 * plen + 6 * 32)]
+        self.payload = [self.pinned[0].array(np.uint8, plen, k * plen) for k in range(4)]
+        self.tails = self.pinned[0].array(np.uint64, 24, 4 * plen).reshape(6, 4)
+        self._dummy = {}
+
+    def _dummy_triple(self, leader, spdz):
+        """dummy_triple in page-locked memory, built once per session (SPDZ: MAC key 1 shared as (1, 0, 0), so the
+        mac plane equals the sh plane)"""
+        key = (bool(leader), bool(spdz))
+        if key not in self._dummy:
+            n, planes = self.r1cs.n, 2 if spdz else 1
+            buf = H.PinnedBuffer(planes * n * 32)
+            self.pinned.append(buf)
+            v = buf.array(np.uint64, planes * n * 4).reshape((planes, n, 4) if spdz else (n, 4))
+            v[...] = FR_R_LIMBS if leader else 0
+            self._dummy[key] = v
+        v = self._dummy[key]
+        return v, v, v
 
     def close(self):
         for p in self.streams:
             _lib.call("mpc_cuda_stream_destroy", p)
         self.streams = []
+        self.payload, self.tails, self._dummy = [], None, {}
+        for b in self.pinned:
+            b.free()
+        self.pinned = []
         for b in [self.za, self.zb, self.lh] + self.parts:
             b.free()
 
@@ -150,48 +175,46 @@ class ProverSession:
             z = np.ascontiguousarray(assignment, dtype=np.uint64).reshape(-1, 4)
         if z.shape[0] != r1cs.num_vars:
             raise ValueError("assignment has %d values, the circuit %d variables" % (z.shape[0], r1cs.num_vars))
-        n = r1cs.n
         if triple is not None:
             tx, ty, tz = triple
-        else:
-            tx, ty, tz = dummy_triple(n, leader)
-            if spdz:                                # MAC key 1 shared as (1, 0, 0): mac plane = sh plane
-                tx, ty, tz = (np.stack([v, v]) for v in (tx, ty, tz))
         zero, one = np.zeros(4, dtype=np.uint64), FR_R_LIMBS
         r = zero if r is None else np.asarray(r, dtype=np.uint64)
         s = zero if s is None else np.asarray(s, dtype=np.uint64)
 
         # ---- witness map: the vectors stay on the device; only wire payloads cross PCIe for the two opens
-        ma, mb, st = H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, planes if spdz else z, r1cs.num_inputs, r1cs.log_n,
-                                              tx, ty, spdz=spdz)
+        if triple is None:
+            tx, ty, tz = self._dummy_triple(leader, spdz)
+        st = H.witness_map_begin_r1cs(r1cs.A, r1cs.B, r1cs.C, planes if spdz else z, r1cs.num_inputs, r1cs.log_n,
+                                      tx, ty, spdz=spdz, masked=False)[2]
         try:
-            def open_masked(masked):
-                val = H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(masked[0] if spdz else masked))), n)
+            for which in (0, 1):
+                pay = H.witness_map_masked_payload(st, which, out=self.payload[which])
+                H.witness_map_open_payloads(st, which, net.exchange(pay))
                 if spdz:                            # batch_open's MAC check, local half + zero test of the sum
-                    dx = H.spdz_mac_check(val, masked[1], leader)
-                    if H.open_sum_deserialize(np.stack(net.exchange(H.fr_serialize(dx))), n).any():
-                        raise H.MpcCudaError("SPDZ MAC check failed on an opened value")
-                return val
+                    dx = H.witness_map_mac_payload(st, which, leader, out=self.payload[2 + which])
+                    H.witness_map_mac_verify(st, net.exchange(dx))
+            h_ptr = H.witness_map_finish_dev(st, tz, None, None, leader)    # SPDZ: [sh | mac] planes, sh first
+            z_ptr, _ = H.witness_map_assignment_dev(st)                     # the sh plane of the assignment, resident
 
-            sx = open_masked(ma)
-            oy = open_masked(mb)
-            h_ptr = H.witness_map_finish_dev(st, tz, sx, oy, leader)        # SPDZ: [sh | mac] planes, sh first
-
-            # ---- scalars of the four MSMs, resident: [assignment[1:] | 1 | 1 | r or s] (leader) and [witness | h]
-            tail_a = np.stack([one, one, r]) if leader else np.zeros((3, 4), dtype=np.uint64)
-            tail_b = np.stack([one, one, s]) if leader else np.zeros((3, 4), dtype=np.uint64)
+            # ---- scalars of the four MSMs, resident: [assignment[1:] | 1 | 1 | r or s] (leader) and [witness | h]:
+            # device-to-device copies of the assignment the witness map uploaded, plus three host elements each
             m = r1cs.num_vars - 1
             sa, sb1, sb2, slh = (p.value for p in self.streams)
-            zab = _cat(z[1:], tail_a, tail_b)               # one staging array: [assignment | tail_a | tail_b]
+            tails = self.tails
+            tails[:] = 0
+            if leader:
+                tails[0:2], tails[2], tails[3:5], tails[5] = one, r, one, s
             h2d = lambda dst, src, nbytes, stream: _lib.call("mpc_cuda_memcpy_h2d", C.c_void_p(dst), src.ctypes.data_as(C.c_void_p),
                                                              C.c_size_t(nbytes), C.c_void_p(stream))
-            h2d(self.za.ptr.value, zab, (m + 3) * 32, sa)
-            h2d(self.zb.ptr.value, zab, m * 32, sb1)
-            h2d(self.zb.ptr.value + m * 32, zab[m + 3:], 3 * 32, sb1)
+            d2d = lambda dst, src, nbytes, stream: _lib.call("mpc_cuda_memcpy_d2d", C.c_void_p(dst), C.c_void_p(src),
+                                                             C.c_size_t(nbytes), C.c_void_p(stream))
+            d2d(self.za.ptr.value, z_ptr + 32, m * 32, sa)
+            h2d(self.za.ptr.value + m * 32, tails[0:3], 3 * 32, sa)
+            d2d(self.zb.ptr.value, z_ptr + 32, m * 32, sb1)
+            h2d(self.zb.ptr.value + m * 32, tails[3:6], 3 * 32, sb1)
             _lib.call("mpc_cuda_stream_sync", C.c_void_p(sb1))   # B2 reads zb on its own stream
-            h2d(self.lh.ptr.value, z[r1cs.num_inputs:], pk.n_l * 32, slh)
-            _lib.call("mpc_cuda_memcpy_d2d", C.c_void_p(self.lh.ptr.value + pk.n_l * 32), C.c_void_p(h_ptr),
-                      C.c_size_t(pk.n_h * 32), C.c_void_p(slh))
+            d2d(self.lh.ptr.value, z_ptr + r1cs.num_inputs * 32, pk.n_l * 32, slh)
+            d2d(self.lh.ptr.value + pk.n_l * 32, h_ptr, pk.n_h * 32, slh)
             H.msm_handle_dev(pk.A, self.za, m + 3, out=self.parts[0], stream=sa)
             H.msm_handle_dev(pk.B1, self.zb, m + 3, out=self.parts[1], stream=sb1)
             H.msm_handle_dev(pk.B2, self.zb, m + 3, out=self.parts[2], stream=sb2)

@@ -418,14 +418,16 @@ def witness_map_begin(a, b, c, tx, ty, spdz=False):
     return ma, mb, WitnessMapState(st.value, n, bool(spdz))
 
 
-def witness_map_begin_r1cs(csr_a, csr_b, csr_c, assignment, num_inputs, log_n, tx, ty, spdz=False):
+def witness_map_begin_r1cs(csr_a, csr_b, csr_c, assignment, num_inputs, log_n, tx, ty, spdz=False, masked=True):
     """the same from the assignment: a = A z, b = B z, c = C z on the device (evaluate_constraint,
-    src/groth16.rs:205-234,263-276,289-293); assignment = instance | witness local values, (cols,4) or (2,cols,4)"""
+    src/groth16.rs:205-234,263-276,289-293); assignment = instance | witness local values, (cols,4) or (2,cols,4).
+    masked=False: the masked vectors stay on the device (returned as None); the opens then go through
+    witness_map_masked_payload / witness_map_open_payloads."""
     z, cols = _planes(assignment, spdz)
     (tx, n), (ty, _) = _planes(tx, spdz), _planes(ty, spdz)
     if n != 1 << log_n or ty.shape != tx.shape or cols != csr_a.cols:
         raise ValueError("witness_map_begin_r1cs: triple planes must have 2^log_n elements and the assignment %d" % csr_a.cols)
-    ma, mb = np.empty_like(tx), np.empty_like(tx)
+    ma, mb = (np.empty_like(tx), np.empty_like(tx)) if masked else (None, None)
     st = C.c_uint64(0)
     _lib.call("mpc_cuda_witness_map_begin_r1cs", C.c_uint64(csr_a.handle), C.c_uint64(csr_b.handle), C.c_uint64(csr_c.handle),
               _p(z), C.c_size_t(num_inputs), C.c_uint32(log_n), _p(tx), _p(ty), C.c_uint32(int(bool(spdz))), _p(ma), _p(mb),
@@ -436,10 +438,10 @@ def witness_map_begin_r1cs(csr_a, csr_b, csr_c, assignment, num_inputs, log_n, t
 def _finish_args(state, tz, sx, oy):
     if not isinstance(state, WitnessMapState) or not state.state:
         raise MpcCudaError("witness_map state already consumed")
-    (tz, n), sx, oy = _planes(tz, state.spdz), _a(sx, 4), _a(oy, 4)
-    if n != state.n or sx.shape != (state.n, 4) or oy.shape != (state.n, 4):
+    (tz, n), sx, oy = _planes(tz, state.spdz), (_a(sx, 4) if sx is not None else None), (_a(oy, 4) if oy is not None else None)
+    if n != state.n or any(v is not None and v.shape != (state.n, 4) for v in (sx, oy)):
         raise ValueError("witness_map_finish: tz / sx / oy must match the begun domain of %d elements" % state.n)
-    return tz, sx, oy
+    return tz, sx, oy                         # sx / oy None: opened through witness_map_open_payloads
 
 
 def witness_map_finish(state, tz, sx, oy, is_leader):
@@ -461,6 +463,77 @@ def witness_map_finish_dev(state, tz, sx, oy, is_leader):
               C.c_uint32(int(bool(is_leader))), C.byref(ptr))
     state.h_ptr = C.cast(ptr, C.c_void_p).value
     return state.h_ptr
+
+
+class PinnedBuffer:
+    """page-locked host memory (mpc_cuda_host_alloc) viewed as numpy arrays: wire payloads and triple shares cross
+    PCIe at the link rate from here, pageable arrays at a fraction of it"""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = C.c_void_p(0)
+        _lib.call("mpc_cuda_host_alloc", C.byref(self.ptr), C.c_size_t(max(self.nbytes, 1)))
+
+    def array(self, dtype=np.uint8, count=None, offset=0):
+        item = np.dtype(dtype).itemsize
+        count = (self.nbytes - offset) // item if count is None else count
+        if offset + count * item > self.nbytes:
+            raise ValueError("view exceeds the pinned buffer")
+        raw = (C.c_uint8 * (count * item)).from_address(self.ptr.value + offset)
+        return np.frombuffer(raw, dtype=dtype, count=count)
+
+    def free(self):
+        if self.ptr.value:
+            _lib.call("mpc_cuda_host_free", self.ptr)
+            self.ptr = C.c_void_p(0)
+
+
+def _payload_out(n, out):
+    if out is None:
+        return np.zeros(8 + 32 * n, dtype=np.uint8)
+    if out.dtype != np.uint8 or out.size != 8 + 32 * n or not out.flags.c_contiguous:
+        raise ValueError("payload buffer must be %d contiguous bytes" % (8 + 32 * n))
+    return out
+
+
+def _payload_ptrs(payloads, n):
+    arrs = [np.ascontiguousarray(p, dtype=np.uint8) for p in payloads]
+    if not arrs or any(a.size != 8 + 32 * n for a in arrs):
+        raise ValueError("expected payloads of %d bytes" % (8 + 32 * n))
+    return arrs, (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def witness_map_masked_payload(state, which, out=None):
+    """the party's broadcast payload of masked_a (which=0) / masked_b (1), straight from the device"""
+    out = _payload_out(state.n, out)
+    _lib.call("mpc_cuda_witness_map_masked_payload", C.c_uint64(state.state), C.c_uint32(which), out.ctypes.data_as(u8p))
+    return out
+
+
+def witness_map_open_payloads(state, which, payloads):
+    """every party's payload of open `which` summed on the device; the opened vector stays in the state"""
+    arrs, ptrs = _payload_ptrs(payloads, state.n)
+    _lib.call("mpc_cuda_witness_map_open_payloads", C.c_uint64(state.state), C.c_uint32(which), ptrs, C.c_uint32(len(arrs)))
+
+
+def witness_map_mac_payload(state, which, is_leader, out=None):
+    out = _payload_out(state.n, out)
+    _lib.call("mpc_cuda_witness_map_mac_payload", C.c_uint64(state.state), C.c_uint32(which), C.c_uint32(int(bool(is_leader))),
+              out.ctypes.data_as(u8p))
+    return out
+
+
+def witness_map_mac_verify(state, payloads):
+    """raises MpcCudaError unless the parties' dx payloads sum to zero everywhere (spdz.rs:177-196)"""
+    arrs, ptrs = _payload_ptrs(payloads, state.n)
+    _lib.call("mpc_cuda_witness_map_mac_verify", C.c_uint64(state.state), ptrs, C.c_uint32(len(arrs)))
+
+
+def witness_map_assignment_dev(state):
+    """device address and length (elements per plane) of the assignment uploaded by witness_map_begin_r1cs"""
+    ptr, cols = u64p(), C.c_size_t(0)
+    _lib.call("mpc_cuda_witness_map_assignment_dev", C.c_uint64(state.state), C.byref(ptr), C.byref(cols))
+    return C.cast(ptr, C.c_void_p).value, cols.value
 
 
 def msm_handle_scalars_dev(handle, scalars_ptr, n, offset=0):
