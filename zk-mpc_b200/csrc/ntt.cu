@@ -130,9 +130,17 @@ DEV void bfly(Fr& u, Fr& v, const Fr* __restrict__ tw, uint32_t k, uint32_t l, b
 // The same butterfly on lazily reduced values (fp.cuh: everything in the tile stays in [0, 2p); one conditional
 // subtraction per addition, none per product): the pass kernel's version.  INV is a compile-time flag so the
 // forward kernels carry no operand selects.
-template <bool INV>
+// ONE: the caller knows k == 0 for every lane (twiddle 1): no product, no table read.
+template <bool INV, bool ONE = false>
 DEV void bfly_lazy(Fr& u, Fr& v, const Fr* __restrict__ tw, uint32_t k, uint32_t l) {
     Fr d;
+    if (ONE) {
+        d = sub_lazy(u, v);
+        u = add_lazy(u, v);
+        fp_detail::cond_sub_2p<consts::FrParams>(d.v);
+        v = d;
+        return;
+    }
     if (INV) {
         const bool swap = k != 0;
         if (swap) k = (1u << (l - 1)) - k;
@@ -214,7 +222,9 @@ __global__ void __launch_bounds__(DEG ? (1 << DEG) : NTT_THREADS,
             Fr x0 = sm_load(sm, E, p0), x1 = sm_load(sm, E, p0 ^ s1), x2 = sm_load(sm, E, p0 ^ s2),
                x3 = sm_load(sm, E, p0 ^ s3);
             const uint32_t k = (qq << log_t) + lo;
-            bfly_lazy<INV>(x0, x2, a.tw[r], k, l0);
+            // last round of the last pass: qq = lo = 0 in every lane, so the first butterfly's twiddle is 1
+            if (last && hbits == 0) bfly_lazy<INV, true>(x0, x2, a.tw[r], 0, l0);
+            else bfly_lazy<INV>(x0, x2, a.tw[r], k, l0);
             bfly_lazy<INV>(x1, x3, a.tw[r], k + (h << log_t), l0);
             bfly_lazy<INV>(x0, x1, a.tw[r + 1], k, l0 - 1);
             bfly_lazy<INV>(x2, x3, a.tw[r + 1], k, l0 - 1);
