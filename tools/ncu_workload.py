@@ -8,6 +8,9 @@ import __graft_entry__ as ge
 pkg = ge.load_package(); H, S, L = pkg.host, pkg.synth, pkg._lib
 H.init(); H.set_party(0, 1)
 what = sys.argv[1]
+for env, opt in (("MSM_AFFINE", "msm_affine"), ("MSM_AFFINE_SPLIT", "msm_affine_split")):      # A/B captures
+    if os.environ.get(env):
+        H.set_option(opt, int(os.environ[env]))
 log_n = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 n = 1 << log_n
 seed = S.bench_seed(log_n)
