@@ -22,7 +22,7 @@ for log_n in [int(x) for x in sys.argv[1:]] or [18, 20, 22, 24]:
         if table:
             h.precompute(0)
         ref = None
-        for mode, name, split in ((1, "off", 0), (2, "one_round", 0), (3, "two_rounds", 0), (3, "two_rounds_staged", 3), (2, "one_round_staged", 3), (0, "auto", 0)):
+        for mode, name, split in ((1, "off", 0), (2, "one_round", 0), (3, "two_rounds", 0), (3, "two_rounds_split", 1), (0, "auto", 0)):
             H.set_option("msm_affine", mode)
             H.set_option("msm_affine_split", split)
             H.set_option("profile", 1)

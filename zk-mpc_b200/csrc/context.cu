@@ -305,7 +305,7 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value) {
         MPC_TRY(enter(nullptr));
         MPC_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
     } else if (!strcmp(name, "msm_affine_split")) {
-        MPC_ARG_CHECK(value >= 0 && value <= 3);
+        MPC_ARG_CHECK(value >= 0 && value <= 2);
         g_opt_msm_affine_split = value;
     } else if (!strcmp(name, "msm_host_chunks")) {
         MPC_ARG_CHECK(value >= 0 && value <= 16);

@@ -615,205 +615,6 @@ __global__ void __launch_bounds__(AFF_THREADS, sizeof(F) > 48 ? 1 : AFF_MIN_BLOC
     }
 }
 
-// ---- the same kernel with the operands staged through shared memory by cp.async -------------------------------
-// The fused kernel above holds every gathered operand in registers from the load to its use, so with 12 warps per
-// SM the gather latency shows (ncu: SM busy 64 %, 72 % of the cycles without an eligible warp).  Here each lane owns
-// a ring of slots in shared memory and keeps the loads of its next pairs in flight as cp.async copies (no registers,
-// no L1 allocation) while the multiplier works on the current pair: the forward pass runs AFF_STAGES_FWD - 1 pairs
-// ahead on x coordinates only (96 B per pair), the backward pass AFF_STAGES_BWD - 1 pairs ahead on whole points
-// (192 B).  A slot is refilled only after the arithmetic that consumed it, so no barrier is needed: a lane reads
-// what it copied itself.  Fq only (the slots of an Fq2 pair would not leave room for three CTAs per SM).
-constexpr int AFF_STAGES_FWD = 4, AFF_STAGES_BWD = 2;
-constexpr int AFF_RING_UNITS = 24;                                   // 16-byte units per lane: 4 x 6 = 2 x 12
-constexpr size_t AFF_RING_BYTES = (size_t)AFF_RING_UNITS * AFF_THREADS * 16;
-
-DEV void cp_async16(uint32_t saddr, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// `units` 16-byte pieces from g into ring units [u0, u0 + units) of this lane
-DEV void ring_fill(uint32_t ring, int u0, const void* g, int units) {
-    const char* src = reinterpret_cast<const char*>(g);
-#pragma unroll
-    for (int w = 0; w < 12; w++)
-        if (w < units) cp_async16(ring + (uint32_t)(u0 + w) * (AFF_THREADS * 16), src + 16 * w);
-}
-// an Fq element (3 units) back from the ring
-template <class F>
-DEV F ring_read(const uint4* ring, int u0) {
-    static_assert(sizeof(F) == 48, "Fq only");
-    F r;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        uint4 t = ring[(u0 + i) * AFF_THREADS];
-        w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-    }
-    return r;
-}
-
-// addresses and flags of pair i: e.x / e.y as in the index list (dense input: positions 2i, 2i+1, no sign, the
-// validity is in the value)
-template <class F, bool GATHER>
-DEV void aff_pair_ptrs(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, size_t i,
-                       const Affine<F>*& pa, const Affine<F>*& pb, bool& va, bool& vb, bool& na, bool& nb) {
-    if (GATHER) {
-        uint2 e = __ldg(reinterpret_cast<const uint2*>(idx) + i);
-        va = e.x != 0xffffffffu;
-        vb = e.y != 0xffffffffu;
-        pa = pts + (e.x & ~msm::DIGIT_NEG);
-        pb = pts + (e.y & ~msm::DIGIT_NEG);
-        na = (e.x & msm::DIGIT_NEG) != 0;
-        nb = (e.y & msm::DIGIT_NEG) != 0;
-    } else {
-        pa = pts + 2 * i;
-        pb = pts + 2 * i + 1;
-        va = vb = true;
-        na = nb = false;
-    }
-}
-
-template <class F, bool GATHER>
-__global__ void __launch_bounds__(AFF_THREADS, AFF_MIN_BLOCKS) k_affine_pairs_staged(const Affine<F>* __restrict__ pts,
-                                                                                    const uint32_t* __restrict__ idx,
-                                                                                    size_t npairs, Affine<F>* __restrict__ out,
-                                                                                    int batch) {
-    extern __shared__ uint4 aff_ring[];
-    const uint32_t lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const uint4* ring = aff_ring + threadIdx.x;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(aff_ring + threadIdx.x);
-    F pre[AFF_B];
-    for (size_t base = warp * (32 * (size_t)batch); base < npairs; base += nwarps * (32 * (size_t)batch)) {
-        // ---- forward: prefix products of the denominators, x coordinates AFF_STAGES_FWD - 1 pairs ahead
-        auto issue_fwd = [&](int k) {
-            const size_t i = base + (size_t)k * 32 + lane;
-            if (k < batch && i < npairs) {
-                const Affine<F>*pa, *pb;
-                bool va, vb, na, nb;
-                aff_pair_ptrs<F, GATHER>(pts, idx, i, pa, pb, va, vb, na, nb);
-                const int u0 = (k % AFF_STAGES_FWD) * 6;
-                if (va) ring_fill(ring_s, u0, &pa->x, 3);
-                if (vb) ring_fill(ring_s, u0 + 3, &pb->x, 3);
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int k = 0; k < AFF_STAGES_FWD - 1; k++) issue_fwd(k);
-        F run = F::one();
-        for (int k = 0; k < batch; k++) {
-            issue_fwd(k + AFF_STAGES_FWD - 1);                  // its slot was consumed in iteration k - 1
-            cp_async_wait<AFF_STAGES_FWD - 1>();
-            const size_t i = base + (size_t)k * 32 + lane;
-            F d = F::one();
-            if (i < npairs) {
-                const Affine<F>*pa, *pb;
-                bool va, vb, na, nb;
-                aff_pair_ptrs<F, GATHER>(pts, idx, i, pa, pb, va, vb, na, nb);
-                const int u0 = (k % AFF_STAGES_FWD) * 6;
-                F ax, bx;
-                if (va) ax = ring_read<F>(ring, u0);
-                if (vb) bx = ring_read<F>(ring, u0 + 3);
-                if (!GATHER) {                                   // (0, 0) = none: x = 0 does not occur on the curve's
-                    if (ax.is_zero()) va = !load_fe_ro(&pa->y).is_zero();      // prime-order subgroup, so y is read rarely
-                    if (bx.is_zero()) vb = !load_fe_ro(&pb->y).is_zero();
-                }
-                if (va && vb) {
-                    F dx = sub(bx, ax);
-                    if (!dx.is_zero()) {
-                        d = dx;
-                    } else {                                     // rare: same x, the y decide between tangent and infinity
-                        F ay = load_fe_ro(&pa->y), by = load_fe_ro(&pb->y);
-                        if (na) ay = neg(ay);
-                        if (nb) by = neg(by);
-                        if (ay == by && !ay.is_zero()) d = dbl(ay);
-                    }
-                }
-            }
-            pre[k] = run;
-            run = mul(run, d);
-        }
-        cp_async_wait<0>();
-        // ---- 1 / (this lane's product) from ONE inversion per warp: inclusive prefix and suffix product scans
-        F pfx = run, sfx = run;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            F up = warp_shfl_up(pfx, off), dn = warp_shfl_down(sfx, off);
-            if (lane >= (uint32_t)off) pfx = mul(pfx, up);
-            if (lane + off < 32) sfx = mul(sfx, dn);
-        }
-        F total = warp_bcast(pfx, 31);
-        F before = warp_shfl_up(pfx, 1), after = warp_shfl_down(sfx, 1);
-        F inv_run = inv_euclid(total);
-        if (lane > 0) inv_run = mul(inv_run, before);
-        if (lane < 31) inv_run = mul(inv_run, after);
-        // ---- backward: whole points AFF_STAGES_BWD - 1 pairs ahead
-        auto issue_bwd = [&](int k) {
-            const size_t i = base + (size_t)k * 32 + lane;
-            if (k >= 0 && i < npairs) {
-                const Affine<F>*pa, *pb;
-                bool va, vb, na, nb;
-                aff_pair_ptrs<F, GATHER>(pts, idx, i, pa, pb, va, vb, na, nb);
-                const int u0 = (k % AFF_STAGES_BWD) * 12;
-                if (GATHER) {
-                    if (va) ring_fill(ring_s, u0, pa, 6);
-                    if (vb) ring_fill(ring_s, u0 + 6, pb, 6);
-                } else {
-                    ring_fill(ring_s, u0, pa, 12);               // the two points are adjacent
-                }
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int k = 0; k < AFF_STAGES_BWD - 1; k++) issue_bwd(batch - 1 - k);
-        for (int k = batch - 1; k >= 0; k--) {
-            issue_bwd(k - (AFF_STAGES_BWD - 1));
-            cp_async_wait<AFF_STAGES_BWD - 1>();
-            const size_t i = base + (size_t)k * 32 + lane;
-            Affine<F> a, b, r;
-            F d = F::one();
-            int kind = 0;
-            if (i < npairs) {
-                const Affine<F>*pa, *pb;
-                bool va, vb, na, nb;
-                aff_pair_ptrs<F, GATHER>(pts, idx, i, pa, pb, va, vb, na, nb);
-                const int u0 = (k % AFF_STAGES_BWD) * 12;
-                if (va) { a.x = ring_read<F>(ring, u0); a.y = ring_read<F>(ring, u0 + 3); if (na) a.y = neg(a.y); }
-                if (vb) { b.x = ring_read<F>(ring, u0 + 6); b.y = ring_read<F>(ring, u0 + 9); if (nb) b.y = neg(b.y); }
-                if (!GATHER) { va = !aff_none(a); vb = !aff_none(b); }
-                if (!va) kind = vb ? 2 : 0;
-                else if (!vb) kind = 1;
-                else {
-                    F dx = sub(b.x, a.x);
-                    if (!dx.is_zero()) { d = dx; kind = 3; }
-                    else if (a.y == b.y && !a.y.is_zero()) { d = dbl(a.y); kind = 4; }
-                }
-            }
-            F dinv = mul(inv_run, pre[k]);
-            inv_run = mul(inv_run, d);
-            if (kind >= 3) {
-                F lam = kind == 3 ? mul(sub(b.y, a.y), dinv) : mul(add(dbl(sqr(a.x)), sqr(a.x)), dinv);
-                F x3 = sub(sub(sqr(lam), a.x), kind == 3 ? b.x : a.x);
-                r.y = sub(mul(lam, sub(a.x, x3)), a.y);
-                r.x = x3;
-            } else if (kind == 1) {
-                r = a;
-            } else if (kind == 2) {
-                r = b;
-            } else {
-                r.x = F::zero();
-                r.y = F::zero();
-            }
-            if (i < npairs) store_pod(out + i, r);
-        }
-        cp_async_wait<0>();
-    }
-}
-
 // buckets split into 2..SMALL_MULTI_MAX tasks: one thread joins them
 template <class F>
 __global__ void __launch_bounds__(ACC_THREADS) k_finalize_small(const uint32_t* __restrict__ small_list,
@@ -1149,8 +950,7 @@ struct MsmJob {
     F *aff_pre = nullptr, *aff_tot = nullptr;    // split rounds: prefix products per pair, products per lane
     cudaStream_t s2 = nullptr;                   // producer stream of the split rounds
     std::vector<cudaEvent_t> events;
-    bool aff_split = false, aff_staged = false;
-    int aff_blocks_s = 1;
+    bool aff_split = false;
     ~MsmJob() {
         for (cudaEvent_t e : events) cudaEventDestroy(e);      // released once the recorded work has completed
     }
@@ -1186,20 +986,7 @@ struct MsmJob {
             // kernel (2^24 points, c = 22: 83.9 vs 78.5 ms; 2^22: 28.1 vs 25.0 ms - the prefix products' round trip
             // through HBM costs more than the overlap wins), so the fused kernel stays the default.
             const size_t pairs0 = (size_t)p.snwin * p.snp / 2;
-            const int64_t split_opt = g_opt_msm_affine_split.load(std::memory_order_relaxed);
-            aff_split = split_opt == 1;
-            aff_staged = false;
-            if constexpr (sizeof(F) == 48) {
-                aff_staged = split_opt == 3;
-                if (aff_staged) {
-                    MPC_CUDA_TRY(cudaFuncSetAttribute(k_affine_pairs_staged<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_RING_BYTES));
-                    MPC_CUDA_TRY(cudaFuncSetAttribute(k_affine_pairs_staged<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_RING_BYTES));
-                    MPC_CUDA_TRY(cudaFuncSetAttribute(k_affine_pairs_staged<F, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                    MPC_CUDA_TRY(cudaFuncSetAttribute(k_affine_pairs_staged<F, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                    MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aff_blocks_s, k_affine_pairs_staged<F, true>, AFF_THREADS, AFF_RING_BYTES));
-                    if (aff_blocks_s < 1) aff_blocks_s = 1;
-                }
-            }
+            aff_split = g_opt_msm_affine_split.load(std::memory_order_relaxed) == 1;
             if (aff_split) {
                 const size_t span = 32 * (size_t)AFF_B;
                 MPC_TRY(s_pre.alloc(&aff_pre, (pairs0 + span - 1) / span * span + span, s));
@@ -1305,18 +1092,8 @@ struct MsmJob {
 
     // one pre-reduction round over `npairs` pairs: the fused kernel, or forward / backward kernels pipelined over
     // two streams in segments of whole warp batches
-    // the cp.async-staged kernel exists for Fq only
-    template <bool GATHER>
-    void launch_staged(const Affine<F>* pts, const uint32_t* idx, size_t npairs, Affine<F>* out, int batch) {
-        if constexpr (sizeof(F) == 48) {
-            k_affine_pairs_staged<F, GATHER><<<dev->sm_count * aff_blocks_s, AFF_THREADS, AFF_RING_BYTES, s>>>(pts, idx, npairs,
-                                                                                                          out, batch);
-        }
-    }
-
     template <bool GATHER>
     int32_t affine_round(const Affine<F>* pts, const uint32_t* idx, size_t npairs, Affine<F>* out, int blocks) {
-        if (aff_staged) blocks = aff_blocks_s;
         // pairs per lane per shared inversion: at least ~4 batches for every resident warp
         const size_t lanes = (size_t)dev->sm_count * blocks * AFF_THREADS;
         size_t b = npairs / (lanes * 4);
@@ -1324,8 +1101,7 @@ struct MsmJob {
         const size_t nwb = (npairs + 32 * (size_t)batch - 1) / (32 * (size_t)batch);       // warp batches
         const int segments = !aff_split ? 0 : nwb >= 4096 ? 8 : nwb >= 8 ? 4 : 1;
         if (segments == 0) {
-            if (aff_staged) launch_staged<GATHER>(pts, idx, npairs, out, batch);
-            else k_affine_pairs<F, GATHER><<<dev->sm_count * blocks, AFF_THREADS, 0, s>>>(pts, idx, npairs, out, batch);
+            k_affine_pairs<F, GATHER><<<dev->sm_count * blocks, AFF_THREADS, 0, s>>>(pts, idx, npairs, out, batch);
             MPC_KERNEL_CHECK();
             return MPC_CUDA_OK;
         }
