@@ -604,6 +604,11 @@ def run_gpu(args):
                 extra["strong"] = bench_strong(pkg, H, S, L, world, log_n, bases_host, scalars_host, args)
             except Exception as e:      # noqa: BLE001 - a failed extra must not lose the headline line
                 extra["strong"] = {"error": str(e)[:300]}
+            if not args.no_prove:
+                try:
+                    extra["prove_one_party_per_gpu"] = bench_prove_per_gpu(pkg, H, S, world)
+                except Exception as e:      # noqa: BLE001
+                    extra["prove_one_party_per_gpu"] = {"error": str(e)[:300]}
         dist.barrier(group=host_group)
 
     # ---- CPU restatement of the reference's path on this box's host cores (rank 0, N = 1 only)
@@ -662,76 +667,106 @@ class _ThreadNet:
         return out
 
 
-def bench_prove(pkg, H, S, args):
-    """prove_hot_path_s: create_proof between synthesis and reveal (src/groth16.rs:100-171) for 3 parties, on the
-    MySecretInputCircuit shape (6574 constraints + 5 inputs -> domain 2^13) and a synthetic 2^20-constraint shape"""
+def _prove_instance(H, S, nc, ni, nv, spdz):
+    """synthetic circuit of the given shape: matrices, proving-key arrays, opened assignment, 3 parties' shares"""
     import numpy as np
+    log_n = max(nc + ni - 1, 0).bit_length()
+    n = 1 << log_n
+    mats = S.r1cs_matrices(0xB10 + log_n, nc, nv)
+
+    def gen(fn, limbs):
+        def g(seed, count):
+            b = fn(seed, count)
+            a = b.download().reshape(count, limbs)
+            b.free()
+            return a
+        return g
+
+    pkarr = S.proving_key_arrays(gen(H.g1_generate, 12), gen(H.g2_generate, 24), 0xB20 + log_n, nv, ni, n)
+    z_open = S.fr_uniform(0xB30, nv)
+    z_open[0] = S.FR_R_LIMBS
+    sub = lambda a, b: H.vec_op("sub", a, b)
+    shares = S.additive_shares(0xB40, z_open, 3, ni, sub)
+    if spdz:            # MAC key 1 shared as (1, 0, 0): the mac planes are additive shares of the same values
+        macs = S.additive_shares(0xB60, z_open, 3, ni, sub)
+        shares = [np.stack([sh, mc]) for sh, mc in zip(shares, macs)]
+    return mats, pkarr, z_open, shares, log_n
+
+
+def _prove_parties(pkg, H, mats, pkarr, ni, nv, shares, devices, spdz, iters=4):
+    """3 party threads, party p on device devices[p]; a proving key / R1CS registration per distinct device.
+    Returns (per-iteration max-over-parties seconds, last results, setup seconds)."""
     G = pkg.groth16
+    parties = len(shares)
+    bar, slots = threading.Barrier(parties), [None] * parties
+    sync = threading.Barrier(parties)
+    res, errs, per_party = [None] * parties, [], [[] for _ in range(parties)]
+    keys, setup = {}, [0.0]
+    owners = {d: min(p for p in range(parties) if devices[p] == d) for d in set(devices)}
+
+    def party(p):
+        try:
+            H.set_party(p, parties)
+            H.set_device(devices[p])
+            if owners[devices[p]] == p:
+                t0 = time.perf_counter()
+                keys[devices[p]] = (G.ProvingKey(**pkarr, table_bits_g1=int(os.environ.get('PK_BITS_G1', '0')),
+                                                 table_bits_g2=int(os.environ.get('PK_BITS_G2', '0'))),
+                                    G.R1CS(*mats, num_inputs=ni, num_vars=nv))
+                setup[0] = max(setup[0], time.perf_counter() - t0)
+            sync.wait()
+            pk, r1cs = keys[devices[p]]
+            session = G.ProverSession(pk, r1cs)       # per-party working set, reused across proofs
+            net = _ThreadNet(p, parties, bar, slots)
+            for _ in range(iters):
+                sync.wait()
+                t0 = time.perf_counter()
+                res[p] = session.prove(shares[p], net, spdz=spdz)
+                per_party[p].append(time.perf_counter() - t0)
+            session.close()
+            sync.wait()
+            if owners[devices[p]] == p:
+                pk.release()
+                r1cs.release()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+            bar.abort()
+            sync.abort()
+
+    ts = [threading.Thread(target=party, args=(p,)) for p in range(parties)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0]
+    H.set_device(0)
+    H.set_party(0, 1)
+    return [max(per_party[p][it] for p in range(parties)) for it in range(iters)], res, setup[0]
+
+
+PROVE_WHAT = ("per proof, all 3 parties concurrently: A z, B z, C z, 3 iFFT, 3 coset FFT, Beaver batch product with 2 opens "
+              "(wire bytes exchanged between the party threads; SPDZ: both planes + the MAC check of each open), coset iFFT, "
+              "4 G1 + 1 G2 MSM")
+
+
+def bench_prove(pkg, H, S, args):
+    """prove_hot_path_s: create_proof between synthesis and reveal (src/groth16.rs:100-171) for 3 parties on one GPU, on
+    the MySecretInputCircuit shape (6574 constraints + 5 inputs -> domain 2^13), the werewolf DivinationCircuit shape
+    under the malicious backend (22 249 constraints, SPDZ planes, BASELINE config 5) and a synthetic 2^20 shape"""
+    import numpy as np
     out = {}
-    parties = 3
-    for name, nc, ni, nv in (("my_secret_input_circuit_2p13", 6574, 5, 6600), ("synthetic_2p20", (1 << 20) - 8, 5, 1 << 20)):
+    for name, nc, ni, nv, spdz in (("my_secret_input_circuit_2p13", 6574, 5, 6600, False),
+                                   ("werewolf_divination_2p15_spdz", 22249, 4, 22300, True),
+                                   ("synthetic_2p20", (1 << 20) - 8, 5, 1 << 20, False)):
         if name == "synthetic_2p20" and args.log_n < 22:
             continue
-        log_n = max(nc + ni - 1, 0).bit_length()
-        n = 1 << log_n
-        mats = S.r1cs_matrices(0xB10 + log_n, nc, nv)
-
-        def gen1(seed, count):
-            b = H.g1_generate(seed, count)
-            a = b.download().reshape(count, 12)
-            b.free()
-            return a
-
-        def gen2(seed, count):
-            b = H.g2_generate(seed, count)
-            a = b.download().reshape(count, 24)
-            b.free()
-            return a
-
-        pkarr = S.proving_key_arrays(gen1, gen2, 0xB20 + log_n, nv, ni, n)
-        z_open = S.fr_uniform(0xB30, nv)
-        z_open[0] = S.FR_R_LIMBS
-        shares = S.additive_shares(0xB40, z_open, parties, ni, lambda a, b: H.vec_op("sub", a, b))
-        t0 = time.perf_counter()
-        pk = G.ProvingKey(**pkarr, table_bits_g1=int(os.environ.get('PK_BITS_G1', '0')), table_bits_g2=int(os.environ.get('PK_BITS_G2', '0')))
-        r1cs = G.R1CS(*mats, num_inputs=ni, num_vars=nv)
-        setup_s = time.perf_counter() - t0
-        iters = 4
-        bar, slots = threading.Barrier(parties), [None] * parties
-        sync = threading.Barrier(parties)
-        res, errs, per_party = [None] * parties, [], [[] for _ in range(parties)]
-
-        def party(p):
-            try:
-                H.set_party(p, parties)
-                H.set_device(0)
-                session = G.ProverSession(pk, r1cs)       # per-party working set, reused across proofs
-                net = _ThreadNet(p, parties, bar, slots)
-                for _ in range(iters):
-                    sync.wait()
-                    t0 = time.perf_counter()
-                    res[p] = session.prove(shares[p], net)
-                    per_party[p].append(time.perf_counter() - t0)
-                session.close()
-            except Exception as e:      # noqa: BLE001
-                errs.append(e)
-                bar.abort()
-                sync.abort()
-
-        ts = [threading.Thread(target=party, args=(p,)) for p in range(parties)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
-        times = [max(per_party[p][it] for p in range(parties)) for it in range(iters)]
-        H.set_party(0, 1)
-        entry = {"prove_hot_path_s": min(times[1:]), "first_call_s": times[0], "parties": parties,
+        mats, pkarr, z_open, shares, log_n = _prove_instance(H, S, nc, ni, nv, spdz)
+        times, res, setup_s = _prove_parties(pkg, H, mats, pkarr, ni, nv, shares, [0, 0, 0], spdz)
+        entry = {"prove_hot_path_s": min(times[1:]), "first_call_s": times[0], "parties": 3, "backend": "spdz" if spdz else "additive",
                  "constraints": nc, "variables": nv, "domain_log2": log_n,
                  "setup_s": setup_s, "setup": "register pk.*_query with window tables + the CSR matrices (once per circuit)",
-                 "what": "per proof, all 3 parties concurrently on one GPU: A z, B z, C z, 3 iFFT, 3 coset FFT, Beaver batch "
-                         "product with 2 opens (wire bytes exchanged between the party threads), coset iFFT, 4 G1 + 1 G2 MSM"}
+                 "what": PROVE_WHAT}
         if not args.no_cpu and name != "synthetic_2p20":
             from oracle import oracle
             zero = np.zeros(4, dtype=np.uint64)
@@ -741,8 +776,8 @@ def bench_prove(pkg, H, S, args):
             t0 = time.perf_counter()
             oracle.groth16_prove(pkarr, mats, ni, z_open, log_n, zero, zero, threads=os.cpu_count() or 1)
             entry["cpu_port_all_cores_s"] = time.perf_counter() - t0
-            entry["cpu_port_note"] = ("the same sequence on plain values through oracle/ (ONE prover; the reference runs it "
-                                      "per party, single-threaded); excludes networking on both sides")
+            entry["cpu_port_note"] = ("the same sequence on plain values through oracle/ (ONE prover, one plane; the reference "
+                                      "runs it per party, single-threaded); excludes networking on both sides")
             # the opened GPU proof equals the CPU one
             acc = {k: res[0][k] for k in ("a", "b", "c")}
             for q in res[1:]:
@@ -750,10 +785,23 @@ def bench_prove(pkg, H, S, args):
                     acc[k] = add(acc[k][0], q[k][0], acc[k][1], q[k][1])
             entry["matches_cpu_proof"] = all(bool(np.array_equal(acc[k][0], exp[k][0])) and acc[k][1] == exp[k][1]
                                              for k in ("a", "b", "c"))
-        pk.release()
-        r1cs.release()
         out[name] = entry
     return out
+
+
+def bench_prove_per_gpu(pkg, H, S, world):
+    """BASELINE config 5: the malicious backend with one party per GPU (party p on device p mod world), all in this
+    process; against the same three parties sharing device 0"""
+    nc, ni, nv = 22249, 4, 22300
+    mats, pkarr, z_open, shares, log_n = _prove_instance(H, S, nc, ni, nv, True)
+    devices = [p % world for p in range(3)]
+    t_split, res_split, _ = _prove_parties(pkg, H, mats, pkarr, ni, nv, shares, devices, True)
+    t_one, res_one, _ = _prove_parties(pkg, H, mats, pkarr, ni, nv, shares, [0, 0, 0], True)
+    import numpy as np
+    same = all(np.array_equal(res_split[p][k][0], res_one[p][k][0]) for p in range(3) for k in ("a", "b", "c"))
+    return {"shape": "werewolf DivinationCircuit (22 249 constraints, domain 2^15), SPDZ planes, 3 parties",
+            "party_devices": devices, "prove_hot_path_s": min(t_split[1:]), "prove_hot_path_s_one_gpu": min(t_one[1:]),
+            "same_shares_as_one_gpu": bool(same), "what": PROVE_WHAT}
 
 
 def bench_strong(pkg, H, S, L, world, log_n, bases_host, scalars_host, args):
