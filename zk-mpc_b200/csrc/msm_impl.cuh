@@ -86,6 +86,7 @@ struct Plan {
     uint32_t hi_bits, lo_bits;   // bucket id = (hi << lo_bits) | lo: level-1 partitions / level-2 bins
     uint32_t chunks;             // level-1 sort chunks per window
     uint32_t task_len;           // max points per accumulate task
+    bool aff_auto = true;        // the pre-reduction rounds were chosen by the size rule: short chunks choose again
     size_t max_tasks;
     uint32_t scan_blocks;        // blocks of the task scan (SCAN_ITEMS buckets each)
     uint32_t red_m, red_t;       // bucket-reduce: red_t chunks of red_m buckets per window
@@ -137,6 +138,7 @@ inline Plan make_plan(size_t n, size_t cap, int sm_count, uint32_t table_c) {
     size_t nbuckets_all = (size_t)p.snwin * p.nb, entries_all = cap * (size_t)p.nwin;
     int64_t aff_opt = g_opt_msm_affine.load(std::memory_order_relaxed);
     p.aff = 0;
+    p.aff_auto = aff_opt == 0;
     if (aff_opt == 0 && entries_all >= 8 * nbuckets_all)
         p.aff = entries_all >= ((size_t)3 << 25) ? 2 : entries_all >= ((size_t)3 << 24) ? 1 : 0;
     else if (aff_opt >= 2) p.aff = (uint32_t)(aff_opt - 1);              // 2 -> one round, 3 -> two rounds
@@ -960,7 +962,7 @@ struct MsmJob {
         return MPC_CUDA_OK;
     }
     size_t nbuckets = 0;
-    int acc_blocks = 1, aff_blocks_g = 1, aff_blocks_d = 1;
+    int acc_blocks = 1, acc_blocks_d = 1, aff_blocks_g = 1, aff_blocks_d = 1;
 
     int32_t begin(size_t n, size_t cap, cudaStream_t stream, const TableRef* t) {
         s = stream;
@@ -1011,9 +1013,10 @@ struct MsmJob {
         MPC_TRY(s_wpart.alloc(&wpart, (size_t)p.snwin * p.sum_parts, s));
         MPC_TRY(s_wsum.alloc(&wsum, p.snwin, s));
         MPC_CUDA_TRY(cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), s));      // all-zero = infinity
-        if (p.aff) MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F, true>, ACC_THREADS, 0));
-        else MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F, false>, ACC_THREADS, 0));
+        MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_d, k_accumulate<F, true>, ACC_THREADS, 0));
+        MPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks, k_accumulate<F, false>, ACC_THREADS, 0));
         if (acc_blocks < 1) acc_blocks = 1;
+        if (acc_blocks_d < 1) acc_blocks_d = 1;
         MPC_TRY(allow_smem(k_finalize_big<F>, ACC_THREADS * sizeof(XYZZ<F>)));
         MPC_TRY(allow_smem(k_window_sum<F>, ACC_THREADS * sizeof(XYZZ<F>)));
         return MPC_CUDA_OK;
@@ -1027,6 +1030,14 @@ struct MsmJob {
         const size_t sn = use_table ? len * p.nwin : len;
         const size_t chunk_len = (sn + p.chunks - 1) / p.chunks;
         const uint32_t merge = nchunks ? 1u : 0u;
+        // pre-reduction rounds of THIS chunk: the plan's (sized for the longest chunk), fewer for a short chunk
+        // whose buckets are too thin for the padding and the shared inversions to pay (same rule as the plan's)
+        uint32_t aff = p.aff;
+        if (aff && p.aff_auto) {
+            const size_t entries = len * (size_t)p.nwin;
+            const uint32_t by_size = entries < 8 * nbuckets ? 0 : entries >= ((size_t)3 << 25) ? 2 : entries >= ((size_t)3 << 24) ? 1 : 0;
+            if (by_size < aff) aff = by_size;
+        }
         profile_begin("msm_sort", s);
         // digits[w*len + i]: with a table the flat array IS one window of nwin*len entries
         k_digits<<<grid_for(len, 256, 8), 256, 0, s>>>(scalars, inf, len, p.c, p.nwin, digits);
@@ -1040,9 +1051,9 @@ struct MsmJob {
                                                                         pairs, len, use_table ? tbl.stride : 0,
                                                                         use_table ? tbl.offset + done : 0);
         MPC_KERNEL_CHECK();
-        if (p.aff) MPC_CUDA_TRY(cudaMemsetAsync(sorted, 0xff, (size_t)p.snwin * p.snp * sizeof(uint32_t), s));   // holes
+        if (aff) MPC_CUDA_TRY(cudaMemsetAsync(sorted, 0xff, (size_t)p.snwin * p.snp * sizeof(uint32_t), s));   // holes
         k_sort2<<<dim3(hbins, p.snwin), SORT2_THREADS, (lbins + SORT2_THREADS) * sizeof(uint32_t), s>>>(
-            pairs, part_start, sn, p.lo_bits, hbins, sorted, bstart, bsize, p.aff, p.aff ? p.snp : sn);
+            pairs, part_start, sn, p.lo_bits, hbins, sorted, bstart, bsize, aff, aff ? p.snp : sn);
         MPC_KERNEL_CHECK();
         k_task_sums<<<p.scan_blocks, 1024, 0, s>>>(bsize, nbuckets, p.task_len, bsums);
         MPC_KERNEL_CHECK();
@@ -1058,18 +1069,18 @@ struct MsmJob {
         // grids sized by the work of THIS chunk (an upper bound of its task count), not by the machine: the MSMs of
         // one proof and of the other parties run side by side on their own streams, and a full-machine grid of
         // mostly idle CTAs in front of them would serialise the small ones
-        const size_t task_bound = ((sn * p.snwin) >> p.aff) / p.task_len + nbuckets + 1;
-        const unsigned acc_grid = (unsigned)std::min<size_t>((size_t)dev->sm_count * acc_blocks,
+        const size_t task_bound = ((sn * p.snwin) >> aff) / p.task_len + nbuckets + 1;
+        const unsigned acc_grid = (unsigned)std::min<size_t>((size_t)dev->sm_count * (aff ? acc_blocks_d : acc_blocks),
                                                              (task_bound + ACC_THREADS - 1) / ACC_THREADS);
         const unsigned fin_small = (unsigned)std::min<size_t>((size_t)dev->sm_count * 2, (nbuckets + ACC_THREADS - 1) / ACC_THREADS);
         const unsigned fin_big = (unsigned)std::min<size_t>((size_t)dev->sm_count, nbuckets);
-        if (p.aff) {
+        if (aff) {
             // pairwise affine additions inside every bucket's padded run, then XYZZ accumulation of what is left
             const size_t slots = (size_t)p.snwin * p.snp;
             MPC_TRY((affine_round<true>(points, sorted, slots / 2, q1, aff_blocks_g)));
-            if (p.aff > 1) MPC_TRY((affine_round<false>(q1, nullptr, slots / 4, q2, aff_blocks_d)));
+            if (aff > 1) MPC_TRY((affine_round<false>(q1, nullptr, slots / 4, q2, aff_blocks_d)));
             k_accumulate<F, true><<<acc_grid, ACC_THREADS, 0, s>>>(
-                p.aff > 1 ? q2 : q1, nullptr, p.snp >> p.aff, p.nb, tasks, counters, buckets, partials, merge);
+                aff > 1 ? q2 : q1, nullptr, p.snp >> aff, p.nb, tasks, counters, buckets, partials, merge);
         } else {
             k_accumulate<F, false><<<acc_grid, ACC_THREADS, 0, s>>>(points, sorted, sn, p.nb, tasks, counters, buckets, partials,
                                                                     merge);
@@ -1398,7 +1409,9 @@ struct CopyLane {
 
 inline uint32_t host_chunks_for(size_t n) {
     int64_t k = g_opt_msm_host_chunks.load(std::memory_order_relaxed);
-    if (k <= 0) k = n >= ((size_t)1 << 23) ? 8 : n >= ((size_t)1 << 21) ? 4 : n >= ((size_t)1 << 19) ? 2 : 1;
+    // measured (tools/e2e_ab.py): 2^24 points 109.8 ms with 4 chunks (3: 110.1, 5: 111.8, 8: 116.4, 1: 130.9),
+    // 2^22 points 38.2 ms with 3 (4: 39.2, 8: 45.8)
+    if (k <= 0) k = n >= ((size_t)1 << 23) ? 4 : n >= ((size_t)1 << 21) ? 3 : n >= ((size_t)1 << 19) ? 2 : 1;
     if (k > 16) k = 16;
     if ((size_t)k > n) k = (int64_t)(n ? n : 1);
     return (uint32_t)k;
@@ -1426,8 +1439,17 @@ int32_t msm_host(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* s
     if (n == 0) {
         MPC_CUDA_TRY(cudaMemsetAsync(res, 0, sizeof(XYZZ<F>), s));
     } else {
+        // Chunk k holds 2^k / (2^K - 1) of the points: only the first (smallest) chunk's copy is exposed, and every
+        // later copy (PCIe moves a point ~2.3x faster than the kernels consume it) hides under the chunk before it
         const uint32_t K = host_chunks_for(n);
-        const size_t cap = (n + K - 1) / K;
+        size_t bound[CopyLane::MAX_CHUNKS + 1];
+        bound[0] = 0;
+        for (uint32_t k = 1; k <= K; k++) {
+            const unsigned __int128 num = (unsigned __int128)n * ((1ull << k) - 1);
+            bound[k] = k == K ? n : (size_t)(num / ((1ull << K) - 1));
+        }
+        size_t cap = 1;
+        for (uint32_t k = 0; k < K; k++) cap = std::max(cap, bound[k + 1] - bound[k]);
         MPC_CUDA_TRY(cudaStreamCreateWithFlags(&lane.s, cudaStreamNonBlocking));
         // the buffers were allocated stream-ordered on s: the copy stream may touch them only after that point
         MPC_CUDA_TRY(cudaEventCreateWithFlags(&lane.ev[CopyLane::MAX_CHUNKS], cudaEventDisableTiming));
@@ -1437,20 +1459,20 @@ int32_t msm_host(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* s
         MsmJob<F> job;
         MPC_TRY(job.begin(n, cap, s, nullptr));
         for (uint32_t k = 0; k < K; k++) {
-            size_t lo = (size_t)k * cap, len = lo + cap <= n ? cap : (lo < n ? n - lo : 0);
-            if (!len) break;
-            MPC_CUDA_TRY(cudaMemcpyAsync(dsc + lo, scalars + lo * 4, len * sizeof(Fr), cudaMemcpyHostToDevice, lane.s));
-            if (di) MPC_CUDA_TRY(cudaMemcpyAsync(di + lo, inf + lo, len, cudaMemcpyHostToDevice, lane.s));
-            MPC_CUDA_TRY(cudaMemcpyAsync(db + lo, bases_xy + lo * (sizeof(Affine<F>) / 8), len * sizeof(Affine<F>),
-                                         cudaMemcpyHostToDevice, lane.s));
+            const size_t lo = bound[k], len = bound[k + 1] - lo;
+            if (len) {
+                MPC_CUDA_TRY(cudaMemcpyAsync(dsc + lo, scalars + lo * 4, len * sizeof(Fr), cudaMemcpyHostToDevice, lane.s));
+                if (di) MPC_CUDA_TRY(cudaMemcpyAsync(di + lo, inf + lo, len, cudaMemcpyHostToDevice, lane.s));
+                MPC_CUDA_TRY(cudaMemcpyAsync(db + lo, bases_xy + lo * (sizeof(Affine<F>) / 8), len * sizeof(Affine<F>),
+                                             cudaMemcpyHostToDevice, lane.s));
+            }
             MPC_CUDA_TRY(cudaEventCreateWithFlags(&lane.ev[k], cudaEventDisableTiming));
             MPC_CUDA_TRY(cudaEventRecord(lane.ev[k], lane.s));
         }
         for (uint32_t k = 0; k < K; k++) {
-            size_t lo = (size_t)k * cap, len = lo + cap <= n ? cap : (lo < n ? n - lo : 0);
-            if (!len) break;
+            const size_t lo = bound[k], len = bound[k + 1] - lo;
             MPC_CUDA_TRY(cudaStreamWaitEvent(s, lane.ev[k], 0));
-            MPC_TRY(job.chunk(db + lo, di ? di + lo : nullptr, dsc + lo, len));
+            if (len) MPC_TRY(job.chunk(db + lo, di ? di + lo : nullptr, dsc + lo, len));
         }
         MPC_TRY(job.finish(res));
     }
