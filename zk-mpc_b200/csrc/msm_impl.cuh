@@ -1409,9 +1409,7 @@ struct CopyLane {
 
 inline uint32_t host_chunks_for(size_t n) {
     int64_t k = g_opt_msm_host_chunks.load(std::memory_order_relaxed);
-    // measured (tools/e2e_ab.py): 2^24 points 109.8 ms with 4 chunks (3: 110.1, 5: 111.8, 8: 116.4, 1: 130.9),
-    // 2^22 points 38.2 ms with 3 (4: 39.2, 8: 45.8)
-    if (k <= 0) k = n >= ((size_t)1 << 23) ? 4 : n >= ((size_t)1 << 21) ? 3 : n >= ((size_t)1 << 19) ? 2 : 1;
+    if (k <= 0) k = n >= ((size_t)1 << 23) ? 6 : n >= ((size_t)1 << 21) ? 4 : n >= ((size_t)1 << 19) ? 2 : 1;
     if (k > 16) k = 16;
     if ((size_t)k > n) k = (int64_t)(n ? n : 1);
     return (uint32_t)k;
@@ -1439,14 +1437,19 @@ int32_t msm_host(const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* s
     if (n == 0) {
         MPC_CUDA_TRY(cudaMemsetAsync(res, 0, sizeof(XYZZ<F>), s));
     } else {
-        // Chunk k holds 2^k / (2^K - 1) of the points: only the first (smallest) chunk's copy is exposed, and every
-        // later copy (PCIe moves a point ~2.3x faster than the kernels consume it) hides under the chunk before it
+        // Chunk sizes double towards the middle and halve again (1 2 4 4 2 1): when the kernels are the slower side
+        // (one GPU per host) only the first, small copy is exposed; when the copies are (eight GPUs sharing the host's
+        // memory and PCIe switches) only the last, small chunk's kernels are; the long middle chunks keep the buckets
+        // dense enough for the pre-reduction
         const uint32_t K = host_chunks_for(n);
         size_t bound[CopyLane::MAX_CHUNKS + 1];
+        uint64_t wsum = 0, wacc = 0;
+        auto weight = [K](uint32_t k) { return (uint64_t)1 << std::min(k, K - 1 - k); };
+        for (uint32_t k = 0; k < K; k++) wsum += weight(k);
         bound[0] = 0;
         for (uint32_t k = 1; k <= K; k++) {
-            const unsigned __int128 num = (unsigned __int128)n * ((1ull << k) - 1);
-            bound[k] = k == K ? n : (size_t)(num / ((1ull << K) - 1));
+            wacc += weight(k - 1);
+            bound[k] = k == K ? n : (size_t)((unsigned __int128)n * wacc / wsum);
         }
         size_t cap = 1;
         for (uint32_t k = 0; k < K; k++) cap = std::max(cap, bound[k + 1] - bound[k]);
