@@ -180,3 +180,40 @@ pub fn poly_mul_vanishing(coeffs: &[Fr], m: usize) -> Vec<Fr> {
     check(unsafe { ffi::mpc_cuda_poly_mul_vanishing(lc.as_ptr(), coeffs.len(), m, out.as_mut_ptr()) });
     frs_from(&out)
 }
+
+/// `R1CStoQAP::witness_map` (src/groth16.rs:240-307) with everything resident between the calls: the two
+/// `batch_open` rounds of the batch product exchange wire payloads only.
+pub struct WitnessMap { state: u64, n: usize }
+impl WitnessMap {
+    /// a = A z, b = B z, c = C z from the party's assignment share, transforms and Beaver masks on the device
+    pub fn begin(csr: [u64; 3], assignment: &[Fr], num_inputs: usize, log_n: u32, tx: &[Fr], ty: &[Fr]) -> Self {
+        let n = 1usize << log_n;
+        assert!(tx.len() == n && ty.len() == n && num_inputs <= assignment.len());
+        let (la, lx, ly) = (fr_limbs(assignment), fr_limbs(tx), fr_limbs(ty));
+        let mut state = 0u64;
+        check(unsafe { ffi::mpc_cuda_witness_map_begin_r1cs(csr[0], csr[1], csr[2], la.as_ptr(), num_inputs, log_n, lx.as_ptr(), ly.as_ptr(), 0,
+                                                           std::ptr::null_mut(), std::ptr::null_mut(), &mut state) });
+        WitnessMap { state, n }
+    }
+    /// the payload this party broadcasts for open `which` (0: a' + x, 1: b' + y), `MpcSerNet::broadcast` format
+    pub fn masked_payload(&self, which: u32) -> Vec<u8> {
+        let mut out = vec![0u8; 8 + 32 * self.n];
+        check(unsafe { ffi::mpc_cuda_witness_map_masked_payload(self.state, which, out.as_mut_ptr()) });
+        out
+    }
+    /// every party's payload of open `which`, as received: summed on the device, kept in the state
+    pub fn open_payloads(&self, which: u32, payloads: &[Vec<u8>]) {
+        assert!(!payloads.is_empty() && payloads.iter().all(|p| p.len() == 8 + 32 * self.n));
+        let ptrs: Vec<*const u8> = payloads.iter().map(|p| p.as_ptr()).collect();
+        check(unsafe { ffi::mpc_cuda_witness_map_open_payloads(self.state, which, ptrs.as_ptr(), ptrs.len() as u32) });
+    }
+    /// Beaver combine, - c, / Z_H, coset iFFT; h stays on the device for `G1Bases::msm_resident`
+    pub fn finish(&self, tz: &[Fr], is_leader: bool) -> *const u64 {
+        assert!(tz.len() == self.n);
+        let lz = fr_limbs(tz);
+        let mut h: *mut u64 = std::ptr::null_mut();
+        check(unsafe { ffi::mpc_cuda_witness_map_finish_dev(self.state, lz.as_ptr(), std::ptr::null(), std::ptr::null(), is_leader as u32, &mut h) });
+        h as *const u64
+    }
+}
+impl Drop for WitnessMap { fn drop(&mut self) { unsafe { ffi::mpc_cuda_witness_map_release(self.state); } } }

@@ -102,6 +102,25 @@ int main(void) {
     orc_fr_vec_serialize(x, m, b2);
     if (memcmp(b1, b2, 8 + 32 * m)) { fprintf(stderr, "fr_serialize mismatch\n"); failures++; }
 
+    /* division by the vanishing polynomial x^64 - 1 from page-locked buffers: q (x^64 - 1) + r must give p back */
+    {
+        const size_t dn = 1000, dm = 64;
+        uint64_t *p = NULL, *q = NULL, *r = NULL, *back = NULL;
+        CHECK(mpc_cuda_host_alloc((void**)&p, dn * 32));
+        CHECK(mpc_cuda_host_alloc((void**)&q, (dn - dm) * 32));
+        CHECK(mpc_cuda_host_alloc((void**)&r, dm * 32));
+        CHECK(mpc_cuda_host_alloc((void**)&back, dn * 32));
+        fr_rand(p, dn, 31);
+        CHECK(mpc_cuda_poly_div_vanishing(p, dn, dm, q, r));
+        /* back = q (x^m - 1); p - back (in place, out = a) must equal r on the low m coefficients and 0 above */
+        CHECK(mpc_cuda_poly_mul_vanishing(q, dn - dm, dm, back));
+        CHECK(mpc_cuda_vec_op(MPC_CUDA_VEC_SUB, p, back, NULL, p, dn));
+        if (memcmp(p, r, dm * 32)) { fprintf(stderr, "poly_div_vanishing: remainder mismatch\n"); failures++; }
+        for (size_t i = dm * 4; i < dn * 4; i++)
+            if (p[i]) { fprintf(stderr, "poly_div_vanishing: high coefficients differ\n"); failures++; break; }
+        CHECK(mpc_cuda_host_free(p)); CHECK(mpc_cuda_host_free(q)); CHECK(mpc_cuda_host_free(r)); CHECK(mpc_cuda_host_free(back));
+    }
+
     /* error convention: non-zero status + message, no abort */
     if (mpc_cuda_set_option("no_such_option", 1) == MPC_CUDA_OK) { fprintf(stderr, "bad option accepted\n"); failures++; }
     if (mpc_cuda_msm_g1_handle(12345678, 0, scalars, 1, got, &gi) != MPC_CUDA_ERR_HANDLE) {
