@@ -86,6 +86,7 @@ int32_t mpc_cuda_host_free(void* hptr);
 int32_t mpc_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* stream);
 int32_t mpc_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream);
 int32_t mpc_cuda_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int32_t mpc_cuda_memset_zero_dev(void* dptr, size_t bytes, void* stream);
 /* extra streams on the calling thread's device, so independent `_dev` calls (the five MSMs of one proof,
  * src/groth16.rs:106-160) overlap; NULL everywhere else means the library's own per-thread stream */
 int32_t mpc_cuda_stream_create(void** stream);
@@ -139,6 +140,9 @@ int32_t mpc_cuda_vec_op(uint32_t op, const uint64_t* a, const uint64_t* b, const
                         uint64_t* out, size_t n);
 int32_t mpc_cuda_vec_op_dev(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c_host,
                             uint64_t* out, size_t n, void* stream);
+/* out[i] = 1 / a[i] for public values (0 stays 0, as ark_ff::batch_inversion ff/src/fields/mod.rs:597-660 leaves it):
+ * the denominators alpha - h of Marlin's r(alpha, .) (arkworks/marlin/src/ahp/mod.rs:357-364).  out may alias a. */
+int32_t mpc_cuda_fr_inverse_dev(const uint64_t* a, uint64_t* out, size_t n, void* stream);
 
 /* ---- share NTT ------------------------------------------------------------------------------
  * Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place over Fr

@@ -636,3 +636,59 @@ def test_witness_map_resident_opens_match_host_route(H, orc, pkg, spdz):
         H.witness_map_masked_payload(st, 0)
     pinned.free()
     r1cs.release()
+
+
+@pytest.mark.parametrize("nc,ni", [(50, 2), (300, 4), (64, 1)])
+def test_marlin_resident_prover_matches_host_route(H, orc, pkg, nc, ni):
+    """marlin.ResidentProver (every vector on the device, only the two Beaver payloads cross PCIe) against the
+    host-array functions, share by share and bit for bit, for 3 party threads; the commitments over powers_of_g summed
+    over the parties equal the plain commitments of the opened oracles"""
+    M, S, K = pkg.marlin, pkg.synth, pkg.kzg
+    parties = 3
+    mats, ints, x, w = helpers.synth_marlin_instance(pkg, orc, 0x7A00 + nc, nc, ni)
+    nh = 1 << max(nc - 1, 0).bit_length()
+    rnd = S.fr_uniform(0x7B00 + nc, 3 * nh + 16)
+    blinders, alpha, etas, mask = rnd[:3], rnd[3], rnd[4:7], rnd[8:8 + 3 * nh]
+    w_sh, bl_sh, mask_sh = (_shares_of(orc, pkg, 0x7C00 + 16 * k, v) for k, v in enumerate((w, blinders, mask)))
+    tx_o, ty_o = S.fr_uniform(0x7D00, 4 * nh), S.fr_uniform(0x7D01, 4 * nh)
+    tz_o = orc.vec_op("mul", tx_o, ty_o)
+    tx, ty, tz = (_shares_of(orc, pkg, 0x7E00 + 16 * k, v) for k, v in enumerate((tx_o, ty_o, tz_o)))
+    pg = orc.g1_generate(0x7F0, 7 * nh)
+    nets = helpers.ThreadNet.make(parties)
+    ready = threading.Barrier(parties)
+    state = {}
+
+    def party(p):
+        H.set_party(p, parties)
+        H.set_device(0)
+        if p == 0:
+            state["index"] = M.Index(mats, nc, ni)
+            state["powers"] = K.Powers(pg, pg[:2])
+        ready.wait()
+        index, leader = state["index"], p == 0
+        z_a, z_b = M.prover_init(index, x, w_sh[p], leader)
+        first = M.prover_first_round(index, x, w_sh[p], z_a, z_b, bl_sh[p], mask_sh[p], leader)
+        second = M.prover_second_round(index, first, x, alpha, etas, nets[p], (tx[p], ty[p], tz[p]), leader)
+        rp = M.ResidentProver(index, parties)
+        res = [rp.rounds(x, w_sh[p], bl_sh[p], mask_sh[p], alpha, etas, nets[p], (tx[p], ty[p], tz[p]), leader,
+                         powers=state["powers"]) for _ in range(2)]          # twice: the buffers are reused
+        rp.close()
+        return dict(host=dict(**first, **second), resident=res)
+
+    outs = _run_parties(party, parties)
+    H.set_party(0, 3)
+    for o in outs:
+        for res in o["resident"]:
+            for key in ("w", "z_a", "z_b", "mask", "z_c", "t", "g_1", "h_1"):
+                assert np.array_equal(res[key], o["host"][key]), key
+            assert res["mul_domain"] == o["host"]["mul_domain"]
+    for key, length in (("w", nh + 1 - ni), ("h_1", 7 * nh), ("g_1", nh - 1), ("mask", 3 * nh)):
+        opened = orc.open_sum(np.stack([o["host"][key] for o in outs]))
+        assert len(opened) == length
+        exp = orc.g1_msm(pg[:length], opened, threads=8)
+        got = _sum_points(orc, [o["resident"][1]["commitments"][key] for o in outs])
+        assert _same(got, exp), key
+    t_len = len(outs[0]["host"]["t"])
+    assert _same(outs[1]["resident"][0]["commitments"]["t"], orc.g1_msm(pg[:t_len], outs[0]["host"]["t"], threads=8))
+    state["index"].release()
+    state["powers"].release()

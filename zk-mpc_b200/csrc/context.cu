@@ -379,6 +379,13 @@ int32_t mpc_cuda_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stre
     return MPC_CUDA_OK;
 }
 
+int32_t mpc_cuda_memset_zero_dev(void* dptr, size_t bytes, void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    MPC_CUDA_TRY(cudaMemsetAsync(dptr, 0, bytes, pick_stream(stream, s)));
+    return MPC_CUDA_OK;
+}
+
 int32_t mpc_cuda_stream_create(void** stream) {
     MPC_ARG_CHECK(stream != nullptr);
     MPC_TRY(enter(nullptr));

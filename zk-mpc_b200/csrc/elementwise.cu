@@ -111,6 +111,15 @@ struct HostStage {
     }
 };
 
+// elementwise inverse of public values (the denominators of Marlin's r(alpha, .), ahp/mod.rs:357-364); zero stays
+// zero as in ark_ff::batch_inversion (ff/src/fields/mod.rs:597-660).  Binary Euclid: no products at all.
+__global__ void __launch_bounds__(128) k_inverse(const Fr* __restrict__ a, Fr* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = load_fe(a + i);
+    store_fe(out + i, x.is_zero() ? x : inv_euclid(x));
+}
+
 }  // namespace
 
 extern "C" {
@@ -233,6 +242,16 @@ int32_t mpc_cuda_spdz_mac_check(const uint64_t* vals, const uint64_t* macs, uint
     MPC_TRY(st.out(n, &dout));
     MPC_TRY(mpc_cuda_spdz_mac_check_dev((const uint64_t*)dv, (const uint64_t*)dm, (uint64_t*)dout, n, is_leader, st.s));
     return st.finish(out, dout, n);
+}
+
+int32_t mpc_cuda_fr_inverse_dev(const uint64_t* a, uint64_t* out, size_t n, void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    if (n == 0) return MPC_CUDA_OK;
+    MPC_ARG_CHECK(a && out);
+    k_inverse<<<(unsigned)((n + 127) / 128), 128, 0, pick_stream(stream, s)>>>((const Fr*)a, (Fr*)out, n);
+    MPC_KERNEL_CHECK();
+    return MPC_CUDA_OK;
 }
 
 int32_t mpc_cuda_vec_op_dev(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c_host, uint64_t* out,

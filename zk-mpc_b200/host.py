@@ -659,3 +659,55 @@ def poly_mul_vanishing(coeffs, m):
     out = np.empty((n + m, 4), dtype=np.uint64)
     _lib.call("mpc_cuda_poly_mul_vanishing", _p(coeffs), C.c_size_t(n), C.c_size_t(m), _p(out))
     return out
+
+
+# ----------------------------------------------------------------------------- device-pointer forms (resident sessions)
+def _dp(ptr):
+    return C.c_void_p(int(ptr)) if ptr is not None else None
+
+
+def dev_zero(ptr, nbytes, stream=None):
+    _lib.call("mpc_cuda_memset_zero_dev", _dp(ptr), C.c_size_t(nbytes), stream)
+
+
+def dev_copy(dst, src, nbytes, stream=None):
+    _lib.call("mpc_cuda_memcpy_d2d", _dp(dst), _dp(src), C.c_size_t(nbytes), stream)
+
+
+def dev_upload(dst, arr, stream=None):
+    arr = np.ascontiguousarray(arr)
+    _lib.call("mpc_cuda_memcpy_h2d", _dp(dst), arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes), stream)
+    return arr                                  # keep the source alive until the caller synchronises
+
+
+def dev_download(src, count, dtype=np.uint64, stream=None):
+    out = np.empty(count, dtype=dtype)
+    _lib.call("mpc_cuda_memcpy_d2h", out.ctypes.data_as(C.c_void_p), _dp(src), C.c_size_t(out.nbytes), stream)
+    _lib.call("mpc_cuda_stream_sync", stream)
+    return out
+
+
+def dev_vec_op(op, a, b, c, out, n, stream=None):
+    c = _a(c, 4) if c is not None else None
+    _lib.call("mpc_cuda_vec_op_dev", C.c_uint32(VEC_OP[op]), _dp(a), _dp(b), _p(c), _dp(out), C.c_size_t(n), stream)
+
+
+def dev_inverse(a, out, n, stream=None):
+    _lib.call("mpc_cuda_fr_inverse_dev", _dp(a), _dp(out), C.c_size_t(n), stream)
+
+
+def dev_spmv(csr, x_ptr, out_ptr, stream=None):
+    _lib.call("mpc_cuda_csr_spmv_dev", C.c_uint64(csr.handle), _dp(x_ptr), C.c_size_t(csr.cols), C.c_uint32(1), _dp(out_ptr),
+              C.c_size_t(csr.rows), stream)
+
+
+def dev_poly_div_vanishing(p, n, m, q, rem, stream=None):
+    _lib.call("mpc_cuda_poly_div_vanishing_dev", _dp(p), C.c_size_t(n), C.c_size_t(m), _dp(q), _dp(rem), stream)
+
+
+def dev_poly_mul_vanishing(p, n, m, out, stream=None):
+    _lib.call("mpc_cuda_poly_mul_vanishing_dev", _dp(p), C.c_size_t(n), C.c_size_t(m), _dp(out), stream)
+
+
+def dev_poly_evaluate(p, n, z, rem, stream=None):
+    _lib.call("mpc_cuda_poly_div_linear_dev", _dp(p), C.c_size_t(n), _p(_a(z, 4)), None, _dp(rem), stream)

@@ -15,6 +15,8 @@ second round follows the untruncated lengths (8 |H| where the plain prover uses 
 truncated like DensePolynomial::from_coefficients_vec does.  Shared - Public and Shared + Public touch the leader's share
 only (`shift`, share/additive.rs:147-152).  Arrays are (n, 4) Montgomery limbs, low degree first.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import host as H
@@ -184,3 +186,220 @@ def prover_second_round(index, first, x_public, alpha, etas, net, triple, is_lea
     q_1[:len(mask)] = _add(q_1[:len(mask)], mask)
     h_1, x_g_1 = H.poly_div_vanishing(q_1, nh)
     return dict(t=t_poly, g_1=x_g_1[1:], h_1=h_1, z_c=z_c, mul_domain=log_n)
+
+
+# ----------------------------------------------------------------------------- the same rounds, resident
+class ResidentProver:
+    """prover_init + first + second round of one party with every vector resident on the device: between the upload of
+    the party's inputs (assignment share, blinders, mask share, triple shares) and the oracles only the two wire
+    payloads of the z_A * z_B Beaver product cross PCIe.  Same arithmetic, in the same order, as the host-array
+    functions above (tests compare the two share by share); buffers are allocated once per index and reused."""
+
+    def __init__(self, index, n_parties=3):
+        self.index, self.parties = index, n_parties
+        nh = index.nh
+        self.n4, self.n8 = 4 * nh, 8 * nh
+        E = lambda count: H.DeviceBuffer(count * 32)
+        self.z = E(index.num_constraints)
+        self.za, self.zb, self.we = E(nh + 1), E(nh + 1), E(nh + 1)
+        self.xe, self.ra, self.rp, self.tp, self.t2 = E(nh), E(nh), E(nh), E(nh), E(nh)
+        self.w, self.zp, self.rem = E(nh + 1), E(nh + 1), E(nh)
+        self.mk = E(3 * nh)
+        self.ea, self.eb, self.sx, self.oy = E(self.n4), E(self.n4), E(self.n4), E(self.n4)
+        self.tx, self.ty, self.tz = E(self.n4), E(self.n4), E(self.n4)
+        self.f = [E(self.n8) for _ in range(4)]
+        self.h1, self.xg = E(7 * nh), E(nh)
+        self.small = E(16)                                       # blinders, x_poly head, scratch elements
+        self.flags = H.DeviceBuffer(16)
+        plen = 8 + 32 * self.n4
+        self.plen = plen
+        self.pay_dev = H.DeviceBuffer(n_parties * plen)
+        self.pinned = H.PinnedBuffer(2 * plen)
+        self.payload = [self.pinned.array(np.uint8, plen, k * plen) for k in range(2)]
+        # public per-index vectors: ones, and the 0/1 mask that clears the input positions of H (k % ratio == 0)
+        ones = np.tile(FR_R_LIMBS, (nh, 1))
+        self.ones = E(nh)
+        H.dev_upload(self.ones.ptr.value, ones)
+        keep = ones.copy()
+        keep[::nh // index.nx] = 0
+        self.keep = E(nh)
+        H.dev_upload(self.keep.ptr.value, keep)
+        H._lib.call("mpc_cuda_stream_sync", None)
+        self.bufs = [self.z, self.za, self.zb, self.we, self.xe, self.ra, self.rp, self.tp, self.t2, self.w, self.zp, self.rem,
+                     self.mk, self.ea, self.eb, self.sx, self.oy, self.tx, self.ty, self.tz, self.h1, self.xg, self.small,
+                     self.flags, self.pay_dev, self.ones, self.keep] + self.f
+
+    def close(self):
+        for b in self.bufs:
+            b.free()
+        self.bufs = []
+        self.pinned.free()
+
+    def _open(self, vec, mask, out, slot, net):
+        """batch_open of vec + mask: payload from the device, exchange, received payloads summed on the device"""
+        n4, plen = self.n4, self.plen
+        H._lib.call("mpc_cuda_beaver_mask_serialize_dev", H._dp(vec), H._dp(mask), C.c_size_t(n4), H._dp(self.pay_dev.ptr.value), None)
+        H._lib.call("mpc_cuda_memcpy_d2h", self.payload[slot].ctypes.data_as(C.c_void_p), H._dp(self.pay_dev.ptr.value),
+                    C.c_size_t(plen), None)
+        H._lib.call("mpc_cuda_stream_sync", None)
+        got = net.exchange(self.payload[slot])
+        if len(got) != self.parties:
+            raise ValueError("expected %d payloads" % self.parties)
+        for p, pay in enumerate(got):
+            pay = np.ascontiguousarray(pay, dtype=np.uint8)
+            if pay.size != plen:
+                raise ValueError("payload of %d bytes, expected %d" % (pay.size, plen))
+            H._lib.call("mpc_cuda_memcpy_h2d", H._dp(self.pay_dev.ptr.value + p * plen), pay.ctypes.data_as(C.c_void_p),
+                        C.c_size_t(plen), None)
+        H._lib.call("mpc_cuda_open_sum_deserialize_dev", H._dp(self.pay_dev.ptr.value), C.c_uint32(self.parties), C.c_size_t(n4),
+                    H._dp(out), H._dp(self.flags.ptr.value), None)
+        flags = H.dev_download(self.flags.ptr.value, 2)          # synchronises: the peers' buffers are free again
+        if flags[1] or flags[0] != np.uint64(0xFFFFFFFFFFFFFFFF):
+            raise H.MpcCudaError("malformed payload in a Beaver open")
+
+    def rounds(self, x_public, w_share, blinders, mask_share, alpha, etas, net, triple, is_leader, powers=None, download=True):
+        """Returns the oracles as host arrays (download=True) and, with `powers` (a kzg.Powers), this party's shares of
+        their commitments over powers_of_g (`commitments`, without the hiding terms)."""
+        ix = self.index
+        nh, nx, nc, n4, n8 = ix.nh, ix.nx, ix.num_constraints, self.n4, self.n8
+        log_h, ratio = nh.bit_length() - 1, nh // nx
+        P = lambda b, k=0: b.ptr.value + 32 * k
+        x, w = _fr(x_public), _fr(w_share)
+        if len(x) != ix.num_inputs or len(x) + len(w) != nc:
+            raise ValueError("instance does not match index")
+        mask_share, bl = _fr(mask_share), _fr(blinders)
+        if len(mask_share) != 3 * nh + 2 * ZK_BOUND - 2 or len(bl) != 3:
+            raise ValueError("mask polynomial / blinders of the wrong length")
+        keepalive = []
+        up = lambda dst, arr: keepalive.append(H.dev_upload(dst, arr))
+        one = FR_R_LIMBS.reshape(1, 4)
+        # ---- prover_init: z_A = A z, z_B = B z
+        up(P(self.z), np.concatenate([x if is_leader else np.zeros_like(x), w]))
+        for buf, m in ((self.za, ix.m[0]), (self.zb, ix.m[1])):
+            H.dev_zero(P(buf), (nh + 1) * 32)
+            H.dev_spmv(m, P(self.z), P(buf))
+        # ---- first round
+        x_poly = _x_poly(ix, x)                                   # |X| public elements: host-side call
+        H.dev_zero(P(self.xe), nh * 32)
+        up(P(self.xe), x_poly)
+        H.ntt_dev(P(self.xe), log_h, "fft")
+        H.dev_vec_op("mul", P(self.xe), P(self.keep), None, P(self.xe), nh)           # no input positions
+        k = np.arange(nh)
+        keep = k % ratio != 0
+        w_evals = np.zeros((nh + 1, 4), dtype=np.uint64)
+        w_evals[:nh][keep] = _pad(w, nh - nx)[(k - k // ratio - 1)[keep]]
+        up(P(self.we), w_evals)
+        up(P(self.small), bl)
+        if is_leader:
+            H.dev_vec_op("sub", P(self.we), P(self.xe), None, P(self.we), nh)
+
+        def blind(buf, j):                                        # + r v_H
+            H.ntt_dev(P(buf), log_h, "ifft")
+            H.dev_copy(P(buf, nh), P(self.small, j), 32)
+            H.dev_vec_op("sub", P(buf), P(self.small, j), None, P(buf), 1)
+
+        blind(self.we, 0)
+        H.dev_poly_div_vanishing(P(self.we), nh + 1, nx, P(self.w), P(self.rem))       # w: nh + 1 - nx coefficients
+        blind(self.za, 1)
+        blind(self.zb, 2)
+        up(P(self.mk), mask_share)
+        H.dev_poly_div_vanishing(P(self.mk), 3 * nh, nh, None, P(self.rem))
+        H.dev_vec_op("sub", P(self.mk), P(self.rem), None, P(self.mk), 1)
+        # ---- second round: z_A * z_B on a domain of 4|H| through Beaver
+        tx, ty, tz = (_fr(v) for v in triple)
+        if any(len(v) != n4 for v in (tx, ty, tz)):
+            raise ValueError("triple shares must hold 4|H| elements")
+        for buf, src in ((self.tx, tx), (self.ty, ty), (self.tz, tz)):
+            up(P(buf), src)
+        for buf, src in ((self.ea, self.za), (self.eb, self.zb)):
+            H.dev_zero(P(buf), n4 * 32)
+            H.dev_copy(P(buf), P(src), (nh + 1) * 32)
+            H.ntt_dev(P(buf), log_h + 2, "fft")
+        self._open(P(self.ea), P(self.tx), P(self.sx), 0, net)
+        self._open(P(self.eb), P(self.ty), P(self.oy), 1, net)
+        zc = self.f[0]                                            # 4|H| of its 8|H|: becomes summed, then padded
+        H._lib.call("mpc_cuda_beaver_combine_dev", H._dp(P(self.tx)), H._dp(P(self.ty)), H._dp(P(self.tz)), H._dp(P(self.sx)),
+                    H._dp(P(self.oy)), H._dp(P(zc)), C.c_size_t(n4), C.c_uint32(int(bool(is_leader))), C.c_uint32(0), None)
+        H.ntt_dev(P(zc), log_h + 2, "ifft")
+        z_c = H.dev_download(P(zc), n4 * 4).reshape(n4, 4) if download else None
+        H.dev_vec_op("mul_const", P(zc), None, etas[2], P(zc), n4)
+        H.dev_vec_op("axpy", P(zc), P(self.za), etas[0], P(zc), nh + 1)
+        H.dev_vec_op("axpy", P(zc), P(self.zb), etas[1], P(zc), nh + 1)
+        H.dev_zero(P(zc, n4), (n8 - n4) * 32)
+        # r(alpha, .) on H: v_H(alpha) / (alpha - h); public, computed by every party
+        H.dev_zero(P(self.ra), nh * 32)
+        if nh > 1:
+            H.dev_copy(P(self.ra, 1), P(self.ones), 32)
+            H.ntt_dev(P(self.ra), log_h, "fft")                   # the elements of H
+        else:
+            H.dev_copy(P(self.ra), P(self.ones), 32)
+        neg_alpha = H.field_op("fr", "neg", _fr(alpha))
+        H.dev_vec_op("axpy", P(self.ra), P(self.ones), neg_alpha, P(self.ra), nh)      # h - alpha
+        H.dev_inverse(P(self.ra), P(self.ra), nh)
+        v_h = np.zeros((nh + 1, 4), dtype=np.uint64)
+        v_h[nh] = FR_R_LIMBS
+        v_h[0:1] = H.field_op("fr", "neg", one)
+        scale = H.field_op("fr", "neg", H.poly_evaluate(v_h, _fr(alpha)[0]).reshape(1, 4))   # -v_H(alpha)
+        H.dev_vec_op("mul_const", P(self.ra), None, scale, P(self.ra), nh)
+        H.dev_copy(P(self.rp), P(self.ra), nh * 32)
+        H.ntt_dev(P(self.rp), log_h, "ifft")
+        # t = sum_M eta_M M^T r(alpha, .), re-indexed
+        H.dev_spmv(ix.mt[0], P(self.ra), P(self.tp))
+        H.dev_vec_op("mul_const", P(self.tp), None, etas[0], P(self.tp), nh)
+        for m, eta in zip(ix.mt[1:], etas[1:]):
+            H.dev_spmv(m, P(self.ra), P(self.t2))
+            H.dev_vec_op("axpy", P(self.tp), P(self.t2), eta, P(self.tp), nh)
+        H.ntt_dev(P(self.tp), log_h, "ifft")
+        # z = w v_X + x
+        H.dev_poly_mul_vanishing(P(self.w), nh + 1 - nx, nx, P(self.zp))
+        if is_leader:
+            if len(x_poly) > 8:
+                raise ValueError("the resident composition stages at most 8 public inputs")
+            up(P(self.small, 8), x_poly)
+            H.dev_vec_op("axpy", P(self.zp), P(self.small, 8), one, P(self.zp), nx)
+        # the multiplication domain of the untruncated shared polynomials: 8|H|
+        def public_len(buf):                                      # from_coefficients_vec: only the top element as a rule
+            if H.dev_download(P(buf, nh - 1), 4).any():
+                return nh
+            return len(_trim_public(H.dev_download(P(buf), nh * 4).reshape(nh, 4)))
+
+        r_len, t_len = public_len(self.rp), public_len(self.tp)
+        mul_n = _domain(max(3 * nh, r_len + n4, t_len + nh + 1))
+        if mul_n != n8:
+            raise H.MpcCudaError("unexpected multiplication domain %d" % mul_n)
+        for buf, src, count in ((self.f[1], self.rp, nh), (self.f[2], self.zp, nh + 1), (self.f[3], self.tp, nh)):
+            H.dev_zero(P(buf), n8 * 32)
+            H.dev_copy(P(buf), P(src), count * 32)
+        for buf in self.f:
+            H.ntt_dev(P(buf), log_h + 3, "fft")
+        H.dev_vec_op("mul", P(self.f[0]), P(self.f[1]), None, P(self.f[0]), n8)
+        H.dev_vec_op("mul", P(self.f[2]), P(self.f[3]), None, P(self.f[2]), n8)
+        H.dev_vec_op("sub", P(self.f[0]), P(self.f[2]), None, P(self.f[0]), n8)
+        H.ntt_dev(P(self.f[0]), log_h + 3, "ifft")
+        H.dev_vec_op("axpy", P(self.f[0]), P(self.mk), one, P(self.f[0]), 3 * nh)
+        H.dev_poly_div_vanishing(P(self.f[0]), n8, nh, P(self.h1), P(self.xg))
+        out = {"mul_domain": log_h + 3}
+        if powers is not None:
+            jac = H.DeviceBuffer(7 * 18 * 8)
+            com = {}
+            for j, (name, buf, off, count) in enumerate((("w", self.w, 0, nh + 1 - nx), ("z_a", self.za, 0, nh + 1),
+                                                         ("z_b", self.zb, 0, nh + 1), ("mask", self.mk, 0, 3 * nh),
+                                                         ("t", self.tp, 0, t_len), ("g_1", self.xg, 1, nh - 1),
+                                                         ("h_1", self.h1, 0, 7 * nh))):
+                if count:
+                    H._lib.call("mpc_cuda_msm_g1_handle_dev", C.c_uint64(powers.g.handle), C.c_size_t(0), H._dp(P(buf, off)),
+                                C.c_size_t(count), H._dp(jac.ptr.value + j * 144), None)
+                else:
+                    H.dev_zero(jac.ptr.value + j * 144, 144)
+                xy, inf = np.zeros(12, dtype=np.uint64), C.c_uint8(0)
+                H._lib.call("mpc_cuda_g1_sum_partials_dev", H._dp(jac.ptr.value + j * 144), C.c_uint32(1), H._p(xy), C.byref(inf), None)
+                com[name] = (xy, inf.value)
+            jac.free()
+            out["commitments"] = com
+        if download:
+            D = lambda buf, count, off=0: H.dev_download(P(buf, off), count * 4).reshape(count, 4)
+            out.update(w=D(self.w, nh + 1 - nx), z_a=D(self.za, nh + 1), z_b=D(self.zb, nh + 1), mask=D(self.mk, 3 * nh),
+                       z_c=z_c, t=D(self.tp, t_len), g_1=D(self.xg, nh - 1, 1), h_1=D(self.h1, 7 * nh))
+        H._lib.call("mpc_cuda_stream_sync", None)
+        del keepalive
+        return out
