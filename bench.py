@@ -595,6 +595,11 @@ def run_gpu(args):
     # ---- the Groth16 prove sequence (x1 / a16): MySecretInputCircuit's shape, 3 parties as 3 threads on this GPU
     if world == 1 and not args.no_prove:
         extra["prove"] = bench_prove(pkg, H, S, args)
+        if args.log_n >= 22:
+            try:
+                extra["marlin"] = bench_marlin(pkg, H, S, 20)
+            except Exception as e:      # noqa: BLE001 - a failed extra must not lose the headline line
+                extra["marlin"] = {"error": str(e)[:300]}
 
     # ---- strong scaling inside ONE process (rank 0 drives all N GPUs through the library's sharded entries)
     if world > 1:
@@ -802,6 +807,86 @@ def bench_prove_per_gpu(pkg, H, S, world):
     return {"shape": "werewolf DivinationCircuit (22 249 constraints, domain 2^15), SPDZ planes, 3 parties",
             "party_devices": devices, "prove_hot_path_s": min(t_split[1:]), "prove_hot_path_s_one_gpu": min(t_one[1:]),
             "same_shares_as_one_gpu": bool(same), "what": PROVE_WHAT}
+
+
+def bench_marlin(pkg, H, S, log_h):
+    """BASELINE config 4's shape: the share-side work of Marlin's AHP rounds 1-2 plus the seven KZG commitment MSMs over
+    powers_of_g (marlin_pc without the hiding terms) on a synthetic R1CS of 2^log_h constraints, 3 parties as 3 threads
+    on this GPU, every vector resident (marlin.ResidentProver); Fiat-Shamir, the third round (public index
+    polynomials) and the openings are not part of this number"""
+    import numpy as np
+    M, K = pkg.marlin, pkg.kzg
+    nh, ni, parties = 1 << log_h, 4, 3
+    nc = nh
+    mats = S.r1cs_matrices(0xC10 + log_h, nc, nc)
+    x = S.fr_uniform(0xC20, ni)
+    x[0] = S.FR_R_LIMBS
+    shares = [dict(w=S.fr_uniform(0xC30 + p, nc - ni), bl=S.fr_uniform(0xC40 + p, 3), mask=S.fr_uniform(0xC50 + p, 3 * nh))
+              for p in range(parties)]
+    rnd = S.fr_uniform(0xC60, 4)
+    alpha, etas = rnd[0], rnd[1:4]
+    t0 = time.perf_counter()
+    index = M.Index(mats, nc, ni)
+    g = H.g1_generate(0xC70, 7 * nh)
+    powers = K.Powers.__new__(K.Powers)
+    powers.g = H.register_bases_dev(g, 7 * nh)
+    powers.g.precompute(0)
+    powers.gamma_g = powers.g
+    setup_s = time.perf_counter() - t0
+    bar, slots = threading.Barrier(parties), [None] * parties
+    sync = threading.Barrier(parties)
+    errs, per_party, coms = [], [[] for _ in range(parties)], [None] * parties
+    iters = 3
+
+    def party(p):
+        try:
+            H.set_party(p, parties)
+            H.set_device(0)
+            leader = p == 0
+            rp = M.ResidentProver(index, parties)
+            # the party's inputs in page-locked memory (triple shares from preprocessing, mask and witness shares)
+            pin = H.PinnedBuffer((4 * nh + 3 * nh + nc) * 32)
+            v = pin.array(np.uint64, 16 * nh).reshape(4 * nh, 4)
+            v[...] = S.FR_R_LIMBS if leader else 0
+            mask = pin.array(np.uint64, 12 * nh, 4 * nh * 32).reshape(3 * nh, 4)
+            mask[...] = shares[p]["mask"]
+            w = pin.array(np.uint64, 4 * (nc - ni), 7 * nh * 32).reshape(nc - ni, 4)
+            w[...] = shares[p]["w"]
+            net = _ThreadNet(p, parties, bar, slots)
+            for _ in range(iters):
+                sync.wait()
+                t0 = time.perf_counter()
+                out = rp.rounds(x, w, shares[p]["bl"], mask, alpha, etas, net, (v, v, v), leader,
+                                powers=powers, download=False)
+                per_party[p].append(time.perf_counter() - t0)
+            coms[p] = out["commitments"]
+            rp.close()
+            pin.free()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+            bar.abort()
+            sync.abort()
+
+    ts = [threading.Thread(target=party, args=(p,)) for p in range(parties)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    H.set_party(0, 1)
+    index.release()
+    powers.g.release()
+    g.free()
+    if errs:
+        raise errs[0]
+    times = [max(per_party[p][it] for p in range(parties)) for it in range(iters)]
+    return {"rounds_and_commitments_s": min(times[1:]), "first_call_s": times[0], "parties": parties, "constraints": nc,
+            "domain_h_log2": log_h, "mul_domain_log2": log_h + 3, "msm_points_per_party": int(15 * nh - ni + 1),
+            "setup_s": setup_s, "t_is_public_and_equal": bool(all(np.array_equal(coms[0]["t"][0], c["t"][0]) for c in coms)),
+            "what": "per party: A z, B z; 3 iFFT |H| with v_H blinding, division by v_X and v_H; z_A z_B as 2 FFT + Beaver batch "
+                    "product (2 opens of 4|H| elements as wire payloads) + iFFT on 4|H|; r(alpha,.) with 2^log_h inversions; t "
+                    "through 3 transposed SpMVs; 4 FFT + 1 iFFT on 8|H| (the shared prover cannot truncate); division by v_H; "
+                    "7 commitment MSMs (|H|, |H|+1, |H|+1, 3|H|, |H|, |H|-1, 7|H| points); no CPU arm at this size "
+                    "(parity: tests/test_gpu_prover.py against oracle.marlin_rounds at 2^6..2^10)"}
 
 
 def bench_strong(pkg, H, S, L, world, log_n, bases_host, scalars_host, args):

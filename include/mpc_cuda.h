@@ -87,6 +87,10 @@ int32_t mpc_cuda_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, void* st
 int32_t mpc_cuda_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, void* stream);
 int32_t mpc_cuda_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 int32_t mpc_cuda_memset_zero_dev(void* dptr, size_t bytes, void* stream);
+/* strided device-to-device copy (height rows of width bytes, pitches in bytes): e.g. the witness values into the
+ * non-input positions of Marlin's domain H (arkworks/marlin/src/ahp/prover.rs:340-349) */
+int32_t mpc_cuda_memcpy2d_d2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                              void* stream);
 /* extra streams on the calling thread's device, so independent `_dev` calls (the five MSMs of one proof,
  * src/groth16.rs:106-160) overlap; NULL everywhere else means the library's own per-thread stream */
 int32_t mpc_cuda_stream_create(void** stream);

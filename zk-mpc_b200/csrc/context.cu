@@ -379,6 +379,16 @@ int32_t mpc_cuda_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stre
     return MPC_CUDA_OK;
 }
 
+int32_t mpc_cuda_memcpy2d_d2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                              void* stream) {
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
+    if (width == 0 || height == 0) return MPC_CUDA_OK;
+    MPC_ARG_CHECK(dst && src && dpitch >= width && spitch >= width);
+    MPC_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToDevice, pick_stream(stream, s)));
+    return MPC_CUDA_OK;
+}
+
 int32_t mpc_cuda_memset_zero_dev(void* dptr, size_t bytes, void* stream) {
     cudaStream_t s;
     MPC_TRY(enter(&s));

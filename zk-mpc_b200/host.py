@@ -674,6 +674,11 @@ def dev_copy(dst, src, nbytes, stream=None):
     _lib.call("mpc_cuda_memcpy_d2d", _dp(dst), _dp(src), C.c_size_t(nbytes), stream)
 
 
+def dev_copy2d(dst, dpitch, src, spitch, width, height, stream=None):
+    _lib.call("mpc_cuda_memcpy2d_d2d", _dp(dst), C.c_size_t(dpitch), _dp(src), C.c_size_t(spitch), C.c_size_t(width),
+              C.c_size_t(height), stream)
+
+
 def dev_upload(dst, arr, stream=None):
     arr = np.ascontiguousarray(arr)
     _lib.call("mpc_cuda_memcpy_h2d", _dp(dst), arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes), stream)

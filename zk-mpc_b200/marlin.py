@@ -203,7 +203,7 @@ class ResidentProver:
         self.z = E(index.num_constraints)
         self.za, self.zb, self.we = E(nh + 1), E(nh + 1), E(nh + 1)
         self.xe, self.ra, self.rp, self.tp, self.t2 = E(nh), E(nh), E(nh), E(nh), E(nh)
-        self.w, self.zp, self.rem = E(nh + 1), E(nh + 1), E(nh)
+        self.w, self.zp, self.rem, self.ws = E(nh + 1), E(nh + 1), E(nh), E(nh)
         self.mk = E(3 * nh)
         self.ea, self.eb, self.sx, self.oy = E(self.n4), E(self.n4), E(self.n4), E(self.n4)
         self.tx, self.ty, self.tz = E(self.n4), E(self.n4), E(self.n4)
@@ -225,7 +225,7 @@ class ResidentProver:
         self.keep = E(nh)
         H.dev_upload(self.keep.ptr.value, keep)
         H._lib.call("mpc_cuda_stream_sync", None)
-        self.bufs = [self.z, self.za, self.zb, self.we, self.xe, self.ra, self.rp, self.tp, self.t2, self.w, self.zp, self.rem,
+        self.bufs = [self.z, self.za, self.zb, self.we, self.xe, self.ra, self.rp, self.tp, self.t2, self.w, self.zp, self.rem, self.ws,
                      self.mk, self.ea, self.eb, self.sx, self.oy, self.tx, self.ty, self.tz, self.h1, self.xg, self.small,
                      self.flags, self.pay_dev, self.ones, self.keep] + self.f
 
@@ -284,11 +284,13 @@ class ResidentProver:
         up(P(self.xe), x_poly)
         H.ntt_dev(P(self.xe), log_h, "fft")
         H.dev_vec_op("mul", P(self.xe), P(self.keep), None, P(self.xe), nh)           # no input positions
-        k = np.arange(nh)
-        keep = k % ratio != 0
-        w_evals = np.zeros((nh + 1, 4), dtype=np.uint64)
-        w_evals[:nh][keep] = _pad(w, nh - nx)[(k - k // ratio - 1)[keep]]
-        up(P(self.we), w_evals)
+        # witness values into the non-input positions of H: position k <- w_ext[k - k / ratio - 1], i.e. every run of
+        # ratio - 1 values lands behind one input slot: a strided copy
+        H.dev_zero(P(self.ws), nh * 32)
+        H.dev_zero(P(self.we), (nh + 1) * 32)
+        if len(w):
+            up(P(self.ws), w)
+        H.dev_copy2d(P(self.we, 1), ratio * 32, P(self.ws), (ratio - 1) * 32, (ratio - 1) * 32, nx)
         up(P(self.small), bl)
         if is_leader:
             H.dev_vec_op("sub", P(self.we), P(self.xe), None, P(self.we), nh)
