@@ -19,6 +19,7 @@ out = H.DeviceBuffer(288 if G2 else 144)
 ref = None
 H.set_option("profile", 1)
 if os.environ.get("MSM_AFFINE"): H.set_option("msm_affine", int(os.environ["MSM_AFFINE"]))
+if os.environ.get("MSM_REDUCE_CHUNK"): H.set_option("msm_reduce_chunk", int(os.environ["MSM_REDUCE_CHUNK"]))
 for tl in task_lens:
     H.set_option("msm_task_len", tl)
     for c in range(max(3, c_lo), min(23, c_hi) + 1):

@@ -100,6 +100,7 @@ extern std::atomic<int64_t> g_opt_msm_task_len;
 extern std::atomic<int64_t> g_opt_msm_host_chunks;
 extern std::atomic<int64_t> g_opt_msm_affine;
 extern std::atomic<int64_t> g_opt_msm_affine_split;
+extern std::atomic<int64_t> g_opt_msm_reduce_chunk;
 extern std::atomic<int64_t> g_opt_profile;
 extern std::atomic<int64_t> g_opt_ntt_generic;
 extern std::atomic<int64_t> g_opt_ntt_occupancy;

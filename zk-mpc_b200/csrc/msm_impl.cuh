@@ -164,6 +164,8 @@ inline Plan make_plan(size_t n, size_t cap, int sm_count, uint32_t table_c) {
     // longer ones once there are enough chunks to fill the machine
     p.red_m = p.nb > (1u << 16) ? 64 : 32;
     while (p.red_m > 4 && (size_t)p.snwin * (p.nb / p.red_m) < (size_t)sm_count * 128) p.red_m >>= 1;
+    const int64_t red_opt = g_opt_msm_reduce_chunk.load(std::memory_order_relaxed);
+    if (red_opt > 0) p.red_m = (uint32_t)red_opt;
     if (p.red_m > p.nb) p.red_m = p.nb;
     p.red_t = p.nb / p.red_m;
     p.sum_parts = (p.red_t + 1023) / 1024;       // <= 1024 chunk results per first-level block
