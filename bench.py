@@ -16,8 +16,10 @@ The JSON line also carries
   extra.table   what the window table behind `value` costs: build time, bytes, break-even MSM count
   extra.ntt_* / extra.beaver_*   the share NTT and Beaver kernels: device-timed, e2e through the host calls, rooflines
   extra.msm_g2  G2 MSM with its own roofline (158 400 IMAD/point)
-  extra.prove   the Groth16 prove sequence (witness map + 4 G1 + 1 G2 MSM, 3 parties as threads) beside the same
-                composition on the CPU restatement
+  extra.prove   the Groth16 prove sequence (witness map + 4 G1 + 1 G2 MSM, 3 parties as threads; additive and SPDZ)
+                beside the same composition on the CPU restatement
+  extra.marlin  Marlin's AHP rounds 1-2 and the seven commitment MSMs on a 2^20-constraint R1CS, vectors resident
+  extra.prove_one_party_per_gpu  (N > 1) the SPDZ prove sequence with party p on device p mod N (BASELINE config 5)
   extra.strong  (N > 1) ONE party's 2^24 MSM and 2^24 / 2^26 NTT sharded over all N GPUs by the library itself
                 (single process, NVLink peer loads/stores inside the cross-stage kernel), strong scaling
 
