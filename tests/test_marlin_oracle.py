@@ -65,3 +65,28 @@ def test_marlin_rounds_identities(orc, pkg, nc, ni):
                     h_r = pow(gen, r, P)
                     t0 += eta * coeff[k] * (v_h(alpha) * pow((alpha - h_r) % P, P - 2, P))
     assert _eval(out["t"], 1) == t0 % P
+
+
+def test_host_side_index_helpers(pkg):
+    """the numpy helpers of marlin.py that run on the host (no GPU): reindex_by_subdomain against the reference's scalar
+    definition (poly/src/domain/mod.rs:195-217), domain sizes, public truncation"""
+    M = pkg.marlin
+
+    def scalar(nh, nx, index):
+        period = nh // nx
+        if index < nx:
+            return index * period
+        i = index - nx
+        return i + i // (period - 1) + 1
+
+    for nh, nx in ((8, 1), (8, 2), (64, 4), (1024, 8), (16, 16)):
+        idx = np.arange(nh)
+        got = M.reindex_by_subdomain(nh, nx, idx)
+        want = [scalar(nh, nx, int(i)) if (nh > nx or i < nx) else None for i in idx]
+        assert [int(g) for g in got] == want
+        assert sorted(int(g) for g in got) == list(range(nh))          # a permutation of H
+    assert [M._domain(k) for k in (0, 1, 2, 3, 4, 5, 1000, 1024, 1025)] == [1, 1, 2, 4, 4, 8, 1024, 1024, 2048]
+    v = np.zeros((6, 4), dtype=np.uint64)
+    v[1, 2] = 7
+    v[3, 0] = 1
+    assert len(M._trim_public(v)) == 4 and len(M._trim_public(np.zeros((3, 4), dtype=np.uint64))) == 0
