@@ -217,6 +217,8 @@ int32_t mpc_cuda_divide_by_vanishing_on_coset_dev(uint64_t* data, uint32_t log_n
  *   _mac_payload      SPDZ only, after _open_payloads: the local half dx = mac_share * val - mac of batch_open's MAC
  *                     check (spdz.rs:177-196) as a payload; _mac_verify sums the parties' dx payloads and returns
  *                     MPC_CUDA_ERR_MAC unless every element is zero.
+ * _release returns the state's buffer to the device's stream-ordered pool on the calling thread's stream: work the
+ * caller put on OTHER streams that still reads h or the assignment must have been synchronised first.
  * _assignment_dev: the assignment _begin_r1cs uploaded (planes x cols, valid until _release), so that the scalar
  * vectors of the a_query / b_query / l_query MSMs (src/groth16.rs:137-160) are device-to-device copies of it. */
 int32_t mpc_cuda_witness_map_begin(const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,

@@ -41,14 +41,16 @@ struct Layout {
     }
 };
 
-int32_t alloc_state(WitnessState* w, uint32_t log_n, uint32_t spdz, size_t cols) {
+// The state's buffer comes from the device's stream-ordered pool (never trimmed): a cudaMalloc / cudaFree pair per
+// proof synchronises the device and stalls the other parties' streams.
+int32_t alloc_state(WitnessState* w, uint32_t log_n, uint32_t spdz, size_t cols, cudaStream_t s) {
     MPC_ARG_CHECK(log_n <= 28);
     w->n = (size_t)1 << log_n;
     w->log_n = log_n;
     w->planes = spdz ? 2 : 1;
     w->cols = cols;
     w->cuda_device = current_device_info()->cuda_device;
-    MPC_CUDA_TRY(cudaMalloc((void**)&w->buf, ((7 * (size_t)w->planes + 2) * w->n + (size_t)w->planes * cols) * sizeof(Fr)));
+    MPC_CUDA_TRY(cudaMallocAsync((void**)&w->buf, ((7 * (size_t)w->planes + 2) * w->n + (size_t)w->planes * cols) * sizeof(Fr), s));
     return MPC_CUDA_OK;
 }
 
@@ -181,7 +183,7 @@ int32_t mpc_cuda_witness_map_begin_ex(const uint64_t* a, const uint64_t* b, cons
     MPC_TRY(enter(&s));
     MPC_ARG_CHECK(a && b && c && tx && ty && state && !masked_a == !masked_b);
     WitnessState w;
-    MPC_TRY(alloc_state(&w, log_n, spdz, 0));
+    MPC_TRY(alloc_state(&w, log_n, spdz, 0, s));
     Layout L(w);
     const size_t bytes = (size_t)w.planes * w.n * sizeof(Fr);
     int32_t rc = MPC_CUDA_OK;
@@ -192,7 +194,7 @@ int32_t mpc_cuda_witness_map_begin_ex(const uint64_t* a, const uint64_t* b, cons
         rc = MPC_CUDA_ERR_CUDA;
     }
     if (rc == MPC_CUDA_OK) rc = begin_tail(w, tx, ty, masked_a, masked_b, state, s);
-    if (rc != MPC_CUDA_OK) cudaFree(w.buf);
+    if (rc != MPC_CUDA_OK) cudaFreeAsync(w.buf, s);
     return rc;
 }
 
@@ -216,7 +218,7 @@ int32_t mpc_cuda_witness_map_begin_r1cs(uint64_t csr_a, uint64_t csr_b, uint64_t
     MPC_ARG_CHECK(rb == rows && rc_ == rows && cb == cols && cc == cols && num_inputs <= cols);
     MPC_ARG_CHECK(log_n <= 28 && rows + num_inputs <= ((size_t)1 << log_n));
     WitnessState w;
-    MPC_TRY(alloc_state(&w, log_n, spdz, cols));
+    MPC_TRY(alloc_state(&w, log_n, spdz, cols, s));
     Layout L(w);
     const size_t n = w.n, pn = (size_t)w.planes * n;
     Fr* z = L.z;                                   // the assignment, planes x cols, kept for _assignment_dev
@@ -239,7 +241,7 @@ int32_t mpc_cuda_witness_map_begin_r1cs(uint64_t csr_a, uint64_t csr_b, uint64_t
             cu(cudaMemcpyAsync(L.a + p * n + rows, z + p * cols, num_inputs * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
         step(rc == MPC_CUDA_OK ? begin_tail(w, tx, ty, masked_a, masked_b, state, s) : rc);
     }
-    if (rc != MPC_CUDA_OK) cudaFree(w.buf);
+    if (rc != MPC_CUDA_OK) cudaFreeAsync(w.buf, s);
     return rc;
 }
 
@@ -258,7 +260,7 @@ int32_t mpc_cuda_witness_map_finish(uint64_t state, const uint64_t* tz, const ui
         set_error("witness_map_finish: device to host copy failed");
         rc = MPC_CUDA_ERR_CUDA;
     }
-    cudaFree(w.buf);            // finish always releases the state
+    cudaFreeAsync(w.buf, s);    // finish always releases the state (the copy out has completed)
     return rc;
 }
 
@@ -378,14 +380,21 @@ int32_t mpc_cuda_witness_map_assignment_dev(uint64_t state, uint64_t** z_dev, si
 }
 
 int32_t mpc_cuda_witness_map_release(uint64_t state) {
-    MPC_TRY(enter(nullptr));
+    cudaStream_t s;
+    MPC_TRY(enter(&s));
     WitnessState w;
     MPC_TRY(take_state(state, true, &w));
     int cur = 0;
     MPC_CUDA_TRY(cudaGetDevice(&cur));
-    MPC_CUDA_TRY(cudaSetDevice(w.cuda_device));
-    cudaFree(w.buf);
-    MPC_CUDA_TRY(cudaSetDevice(cur));
+    if (cur == w.cuda_device) {
+        // stream-ordered: everything this thread enqueued on its stream has finished with the buffer by then; readers
+        // on other streams (the MSMs fed from h / the assignment) were synchronised by the caller
+        MPC_CUDA_TRY(cudaFreeAsync(w.buf, s));
+    } else {                                       // released from a thread bound to another device: synchronous
+        MPC_CUDA_TRY(cudaSetDevice(w.cuda_device));
+        cudaFree(w.buf);
+        MPC_CUDA_TRY(cudaSetDevice(cur));
+    }
     return MPC_CUDA_OK;
 }
 
