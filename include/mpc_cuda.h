@@ -57,6 +57,8 @@ int32_t mpc_cuda_device_count(void);
  *                      segment j+1 under the multiplier-bound addition pass of segment j): 0 or 2 = one fused
  *                      kernel (default: the split measured 7% slower at 2^24), 1 = split
  *   "msm_reduce_chunk" buckets per thread of the bucket reduction (a power of two; 0 = automatic)
+ *   "msm_reduce_warp_max" the bucket reduction runs one WARP per chunk (warp-cooperative group law: shorter serial
+ *                      chains, 32x the threads) while it has at most this many chunks; 0 = automatic
  *   "msm_host_chunks"  point-range chunks a host-buffer MSM is streamed in (copy/compute overlap), 1..16; the chunk
  *                      sizes double towards the middle and halve again (1 2 4 4 2 1), so that neither the first copy
  *                      nor the last chunk's kernels are long

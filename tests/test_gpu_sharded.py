@@ -25,7 +25,7 @@ def H(pkg):
 @pytest.fixture(autouse=True)
 def _reset_options(H):
     yield
-    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks", "msm_affine", "msm_affine_split", "msm_reduce_chunk", "ntt_graph"):
+    for name in ("msm_window_bits", "msm_task_len", "msm_host_chunks", "msm_affine", "msm_affine_split", "msm_reduce_chunk", "msm_reduce_warp_max", "ntt_graph"):
         H.set_option(name, 0)
 
 

@@ -101,6 +101,7 @@ extern std::atomic<int64_t> g_opt_msm_host_chunks;
 extern std::atomic<int64_t> g_opt_msm_affine;
 extern std::atomic<int64_t> g_opt_msm_affine_split;
 extern std::atomic<int64_t> g_opt_msm_reduce_chunk;
+extern std::atomic<int64_t> g_opt_msm_reduce_warp_max;
 extern std::atomic<int64_t> g_opt_profile;
 extern std::atomic<int64_t> g_opt_ntt_generic;
 extern std::atomic<int64_t> g_opt_ntt_occupancy;

@@ -304,6 +304,9 @@ int32_t mpc_cuda_set_option(const char* name, int64_t value) {
         MPC_ARG_CHECK(value == 32 || value == 64 || value == 128);
         MPC_TRY(enter(nullptr));
         MPC_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    } else if (!strcmp(name, "msm_reduce_warp_max")) {
+        MPC_ARG_CHECK(value >= 0 && value <= (1 << 20));
+        g_opt_msm_reduce_warp_max = value;
     } else if (!strcmp(name, "msm_reduce_chunk")) {
         MPC_ARG_CHECK(value >= 0 && value <= 4096 && (value & (value - 1)) == 0);
         g_opt_msm_reduce_chunk = value;

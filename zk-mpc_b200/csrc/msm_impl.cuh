@@ -1145,8 +1145,11 @@ struct MsmJob {
         profile_begin("msm_reduce", s);
         const size_t tree_smem = ACC_THREADS * sizeof(XYZZ<F>);
         uint32_t red_threads = p.snwin * p.red_t;
-        if (red_threads <= 128) {                  // 32x the threads: only while that stays a sliver of the machine,
-                                                   // the MSMs of one proof and of the other parties run concurrently
+        const int64_t warp_opt = g_opt_msm_reduce_warp_max.load(std::memory_order_relaxed);
+        // one warp per chunk (32x the threads) only while that stays a sliver of the machine: the MSMs of one proof and of
+        // the other parties run concurrently.  3-party prove, 2^13 / 2^15 SPDZ: 6.26 / 13.3 ms with a limit of 128 chunks,
+        // 6.19 / 12.8 at 512, 5.8 / 16.8 at 8192
+        if (red_threads <= (uint32_t)(warp_opt > 0 ? warp_opt : 512)) {
             k_bucket_reduce_warp<F><<<(red_threads * 32 + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(
                 buckets, p.snwin, p.nb, p.red_m, p.red_t, chunk_res);
         } else {

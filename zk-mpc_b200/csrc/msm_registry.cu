@@ -11,6 +11,7 @@ std::atomic<int64_t> g_opt_msm_host_chunks{0};
 std::atomic<int64_t> g_opt_msm_affine{0};
 std::atomic<int64_t> g_opt_msm_affine_split{0};
 std::atomic<int64_t> g_opt_msm_reduce_chunk{0};
+std::atomic<int64_t> g_opt_msm_reduce_warp_max{0};
 
 static std::mutex g_bases_mu;
 static std::unordered_map<uint64_t, BaseRef> g_bases;
