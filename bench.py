@@ -838,6 +838,7 @@ def bench_marlin(pkg, H, S, log_h):
     bar, slots = threading.Barrier(parties), [None] * parties
     sync = threading.Barrier(parties)
     errs, per_party, coms = [], [[] for _ in range(parties)], [None] * parties
+    per_party_rounds = [[] for _ in range(parties)]
     iters = 3
 
     def party(p):
@@ -860,6 +861,9 @@ def bench_marlin(pkg, H, S, log_h):
                 t0 = time.perf_counter()
                 out = rp.rounds(x, w, shares[p]["bl"], mask, alpha, etas, net, (v, v, v), leader,
                                 powers=powers, download=False)
+                per_party_rounds[p].append(time.perf_counter() - t0)
+                rp.open_combination([(name, etas[k % 3]) for k, name in enumerate(("w", "z_a", "z_b", "mask", "t", "g_1", "h_1"))],
+                                    alpha, powers)
                 per_party[p].append(time.perf_counter() - t0)
             coms[p] = out["commitments"]
             rp.close()
@@ -881,13 +885,17 @@ def bench_marlin(pkg, H, S, log_h):
     if errs:
         raise errs[0]
     times = [max(per_party[p][it] for p in range(parties)) for it in range(iters)]
-    return {"rounds_and_commitments_s": min(times[1:]), "first_call_s": times[0], "parties": parties, "constraints": nc,
+    times_rounds = [max(per_party_rounds[p][it] for p in range(parties)) for it in range(iters)]
+    return {"rounds_commitments_opening_s": min(times[1:]), "rounds_and_commitments_s": min(times_rounds[1:]),
+            "first_call_s": times[0], "parties": parties, "constraints": nc,
             "domain_h_log2": log_h, "mul_domain_log2": log_h + 3, "msm_points_per_party": int(15 * nh - ni + 1),
             "setup_s": setup_s, "t_is_public_and_equal": bool(all(np.array_equal(coms[0]["t"][0], c["t"][0]) for c in coms)),
             "what": "per party: A z, B z; 3 iFFT |H| with v_H blinding, division by v_X and v_H; z_A z_B as 2 FFT + Beaver batch "
                     "product (2 opens of 4|H| elements as wire payloads) + iFFT on 4|H|; r(alpha,.) with 2^log_h inversions; t "
                     "through 3 transposed SpMVs; 4 FFT + 1 iFFT on 8|H| (the shared prover cannot truncate); division by v_H; "
-                    "7 commitment MSMs (|H|, |H|+1, |H|+1, 3|H|, |H|, |H|-1, 7|H| points); no CPU arm at this size "
+                    "7 commitment MSMs (|H|, |H|+1, |H|+1, 3|H|, |H|, |H|-1, 7|H| points); then one opening: the linear "
+                    "combination of the seven oracles, its witness polynomial / (x - alpha), evaluation and witness commitment "
+                    "(7|H| points); no CPU arm at this size "
                     "(parity: tests/test_gpu_prover.py against oracle.marlin_rounds at 2^6..2^10)"}
 
 

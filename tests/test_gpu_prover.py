@@ -672,8 +672,16 @@ def test_marlin_resident_prover_matches_host_route(H, orc, pkg, nc, ni):
         rp = M.ResidentProver(index, parties)
         res = [rp.rounds(x, w_sh[p], bl_sh[p], mask_sh[p], alpha, etas, nets[p], (tx[p], ty[p], tz[p]), leader,
                          powers=state["powers"]) for _ in range(2)]          # twice: the buffers are reused
+        # the opening phase on the resident oracles against the host-array route: LC, witness, evaluation, commitment
+        terms = [("w", etas[0]), ("z_b", etas[1]), ("h_1", etas[2]), ("g_1", alpha), ("t", blinders[0])]
+        opened = rp.open_combination(terms, alpha, state["powers"])
+        host_polys = dict(**first, **second)
+        lc = np.zeros((0, 4), dtype=np.uint64)
+        for name, coeff in terms:
+            lc = K.add_assign_scaled(lc, coeff, host_polys[name])
+        host_open = K.open(state["powers"], lc, alpha)
         rp.close()
-        return dict(host=dict(**first, **second), resident=res)
+        return dict(host=host_polys, resident=res, opened=opened, host_open=(host_open[0], H.poly_evaluate(lc, alpha)), lc=lc)
 
     outs = _run_parties(party, parties)
     H.set_party(0, 3)
@@ -688,6 +696,10 @@ def test_marlin_resident_prover_matches_host_route(H, orc, pkg, nc, ni):
         exp = orc.g1_msm(pg[:length], opened, threads=8)
         got = _sum_points(orc, [o["resident"][1]["commitments"][key] for o in outs])
         assert _same(got, exp), key
+    for o in outs:                                               # resident opening = host-array opening, per share
+        assert _same(o["opened"][0], o["host_open"][0]) and np.array_equal(o["opened"][1], o["host_open"][1])
+    lc_open = orc.open_sum(np.stack([o["lc"] for o in outs]))
+    assert np.array_equal(orc.open_sum(np.stack([o["opened"][1][None] for o in outs]))[0], orc.horner(lc_open, alpha))
     t_len = len(outs[0]["host"]["t"])
     assert _same(outs[1]["resident"][0]["commitments"]["t"], orc.g1_msm(pg[:t_len], outs[0]["host"]["t"], threads=8))
     state["index"].release()

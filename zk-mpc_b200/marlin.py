@@ -405,3 +405,36 @@ class ResidentProver:
         H._lib.call("mpc_cuda_stream_sync", None)
         del keepalive
         return out
+
+    def open_combination(self, terms, point, powers):
+        """The opening phase on the resident oracles of the last `rounds` call: the linear combination
+        sum_i coeff_i * poly_i (marlin/mod.rs:213-306 accumulates `poly += (coeff, poly)`, dense.rs:345-372), its witness
+        polynomial / (x - point) and evaluation (kzg10/mod.rs:205-290, univariate_div_qr on shares), and the witness
+        commitment over powers_of_g.  terms = [(name, public coeff)], names from w z_a z_b mask t g_1 h_1.
+        Returns (this party's share of the witness commitment, its share of the evaluation)."""
+        nh, nx = self.index.nh, self.index.nx
+        P = lambda b, k=0: b.ptr.value + 32 * k
+        polys = {"w": (self.w, 0, nh + 1 - nx), "z_a": (self.za, 0, nh + 1), "z_b": (self.zb, 0, nh + 1), "mask": (self.mk, 0, 3 * nh),
+                 "t": (self.tp, 0, nh), "g_1": (self.xg, 1, nh - 1), "h_1": (self.h1, 0, 7 * nh)}
+        if not terms:
+            raise ValueError("empty combination")
+        acc, wit = self.f[1], self.f[2]                           # 8|H| scratch of the second round
+        n = max(polys[name][2] for name, _ in terms)
+        H.dev_zero(P(acc), n * 32)
+        for name, coeff in terms:
+            buf, off, count = polys[name]
+            if count:
+                H.dev_vec_op("axpy", P(acc), P(buf, off), _fr(coeff), P(acc), count)
+        H._lib.call("mpc_cuda_poly_div_linear_dev", H._dp(P(acc)), C.c_size_t(n), H._p(_fr(point)), H._dp(P(wit)) if n > 1 else None,
+                    H._dp(P(self.small, 12)), None)
+        value = H.dev_download(P(self.small, 12), 4)
+        xy, inf = np.zeros(12, dtype=np.uint64), C.c_uint8(0)
+        if n > 1:
+            jac = H.DeviceBuffer(144)
+            H._lib.call("mpc_cuda_msm_g1_handle_dev", C.c_uint64(powers.g.handle), C.c_size_t(0), H._dp(P(wit)), C.c_size_t(n - 1),
+                        H._dp(jac.ptr.value), None)
+            H._lib.call("mpc_cuda_g1_sum_partials_dev", H._dp(jac.ptr.value), C.c_uint32(1), H._p(xy), C.byref(inf), None)
+            jac.free()
+        else:
+            inf = C.c_uint8(1)
+        return (xy, inf.value), value
