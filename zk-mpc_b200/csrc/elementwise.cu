@@ -112,12 +112,34 @@ struct HostStage {
 };
 
 // elementwise inverse of public values (the denominators of Marlin's r(alpha, .), ahp/mod.rs:357-364); zero stays
-// zero as in ark_ff::batch_inversion (ff/src/fields/mod.rs:597-660).  Binary Euclid: no products at all.
+// zero as in ark_ff::batch_inversion (ff/src/fields/mod.rs:597-660), whose trick this is: every thread takes INV_BATCH
+// strided elements, multiplies the non-zero ones up, inverts the product once (binary Euclid) and peels the
+// individual inverses off backwards: 3 products per element instead of an inversion.
+constexpr int INV_BATCH = 8;
 __global__ void __launch_bounds__(128) k_inverse(const Fr* __restrict__ a, Fr* __restrict__ out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr x = load_fe(a + i);
-    store_fe(out + i, x.is_zero() ? x : inv_euclid(x));
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (tid >= n) return;
+    Fr x[INV_BATCH], pre[INV_BATCH];
+    Fr run = Fr::one();
+#pragma unroll
+    for (int k = 0; k < INV_BATCH; k++) {
+        const size_t i = tid + (size_t)k * stride;
+        x[k] = i < n ? load_fe(a + i) : Fr::zero();
+        pre[k] = run;
+        if (!x[k].is_zero()) run = mul(run, x[k]);
+    }
+    Fr inv_run = inv_euclid(run);                  // run is a product of non-zero elements (1 if there were none)
+#pragma unroll
+    for (int k = INV_BATCH - 1; k >= 0; k--) {
+        const size_t i = tid + (size_t)k * stride;
+        if (i >= n) continue;
+        if (x[k].is_zero()) {
+            store_fe(out + i, x[k]);
+        } else {
+            store_fe(out + i, mul(inv_run, pre[k]));
+            inv_run = mul(inv_run, x[k]);
+        }
+    }
 }
 
 }  // namespace
@@ -249,7 +271,8 @@ int32_t mpc_cuda_fr_inverse_dev(const uint64_t* a, uint64_t* out, size_t n, void
     MPC_TRY(enter(&s));
     if (n == 0) return MPC_CUDA_OK;
     MPC_ARG_CHECK(a && out);
-    k_inverse<<<(unsigned)((n + 127) / 128), 128, 0, pick_stream(stream, s)>>>((const Fr*)a, (Fr*)out, n);
+    const size_t threads = (n + INV_BATCH - 1) / INV_BATCH;
+    k_inverse<<<(unsigned)((threads + 127) / 128), 128, 0, pick_stream(stream, s)>>>((const Fr*)a, (Fr*)out, n);
     MPC_KERNEL_CHECK();
     return MPC_CUDA_OK;
 }
